@@ -1,0 +1,505 @@
+/*
+ * agar_b200.cu — kernels + the C ABI (include/agar_b200.h) of the B200-native batched agar.io step.
+ * Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false -shared -Xcompiler -fPIC
+ * No torch, no CPU fallback: every entry point runs CUDA kernels on the handle's device or fails.
+ */
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/agar_b200.h"
+#include "../../include/agar_layout.h"
+#include "agar_bots.cuh"
+#include "agar_dev.cuh"
+
+extern __shared__ __align__(16) uint8_t g_smem[];
+
+/* ------------------------------------------------------------------ staging: HBM <-> shared memory, whole CTA */
+__device__ __forceinline__ void stage_in(const DevParams& P, const uint8_t* state, int env0, int n_here, bool zero) {
+    const int chunks = (int)(P.L.record_bytes / 8);
+    const int total = n_here * chunks;
+    const uint2* src = (const uint2*)(state + (size_t)env0 * P.L.record_bytes);
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        int e = i / chunks, w = i - e * chunks;
+        uint2 v = zero ? make_uint2(0u, 0u) : src[i];
+        ((uint2*)(g_smem + (size_t)e * P.rec_stride))[w] = v;
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void stage_out(const DevParams& P, uint8_t* state, int env0, int n_here) {
+    __syncthreads();
+    const int chunks = (int)(P.L.record_bytes / 8);
+    const int total = n_here * chunks;
+    uint2* dst = (uint2*)(state + (size_t)env0 * P.L.record_bytes);
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        int e = i / chunks, w = i - e * chunks;
+        dst[i] = ((const uint2*)(g_smem + (size_t)e * P.rec_stride))[w];
+    }
+}
+template <int W>
+__device__ __forceinline__ void bind_ctx(Ctx<W>& c, const DevParams& P, int tile_id, int tiles, int env) {
+    c.lane = c.t.thread_rank();
+    c.env_id = (uint32_t)(P.first_env + (uint64_t)env);
+    c.rec = g_smem + (size_t)tile_id * P.rec_stride;
+    c.h = (AgarEnvHeader*)(c.rec + P.L.off_header);
+    c.pl = (AgarPlayer*)(c.rec + P.L.off_players);
+    c.cells = (AgarCell*)(c.rec + P.L.off_cells);
+    c.vir = (AgarMote*)(c.rec + P.L.off_viruses);
+    c.blob = (AgarMote*)(c.rec + P.L.off_blobs);
+    c.fat = (AgarFatPellet*)(c.rec + P.L.off_fat);
+    c.pel = (uint32_t*)(c.rec + P.L.off_pellets);
+    c.hist = (float*)(c.rec + P.L.off_hist);
+    c.ev = (AgarEvent*)(c.rec + P.L.off_events);
+    c.scratch = g_smem + (size_t)tiles * P.rec_stride + (size_t)tile_id * P.scratch_bytes;
+}
+
+/* ------------------------------------------------------------------ the step kernel */
+template <int W, bool FULL>
+__global__ void __launch_bounds__(128)
+k_main(const __grid_constant__ DevParams P, uint8_t* __restrict__ state, const float* __restrict__ actions,
+       float* __restrict__ obs, int n_frames, int n_dec, int flags, uint32_t dec_base) {
+    const int tiles = blockDim.x / W;
+    const int env0 = blockIdx.x * tiles;
+    const int n_here = min(tiles, P.n_envs - env0);
+    stage_in(P, state, env0, n_here, false);
+    const int tile_id = threadIdx.x / W;
+    if (tile_id < n_here) {
+        Ctx<W> c(cg::tiled_partition<W>(cg::this_thread_block()));
+        const int env = env0 + tile_id;
+        bind_ctx(c, P, tile_id, tiles, env);
+        const int A = P.L.n_agents, K = P.L.n_players, SL = P.L.state_len;
+        float* obs_env = obs ? obs + (size_t)env * A * SL : nullptr;
+        for (int d = 0; d < n_dec; ++d) {
+            if (flags & KF_OBS_BEFORE)
+                for (int a = 0; a < A; ++a) nn_turn_begin<W, FULL>(c, P, a, obs_env ? obs_env + (size_t)a * SL : nullptr);
+            for (int f = 0; f < n_frames; ++f) {
+                if (c.lane == 0) c.h->n_events = 0;
+                for (int k = 0; k < K; ++k) {
+                    if (!FULL || P.cfg.bot_type[k] == AGAR_BOT_NN) {
+                        nn_turn_begin<W, FULL>(c, P, k, nullptr);
+                        if (c.lane == 0) {
+                            float act[4] = {0.f, 0.f, 0.f, 0.f};
+                            if (c.pl[k].bot.need_action) {
+                                if (flags & KF_RANDOM_ACTIONS) { /* random-action driver */
+                                    uint32_t w[4];
+                                    philox(dec_base + (uint32_t)d, 7u, c.env_id, (uint32_t)k, (uint32_t)P.seed,
+                                           (uint32_t)(P.seed >> 32), w);
+                                    for (int i = 0; i < 4; ++i) act[i] = (float)(w[i] >> 8) * (1.0f / 16777216.0f);
+                                } else {
+                                    const float* ap = actions + ((size_t)env * A + k) * 4;
+                                    for (int i = 0; i < 4; ++i) act[i] = ap[i];
+                                }
+                            }
+                            nn_turn_end(c, P, k, act);
+                        }
+                        c.t.sync();
+                    } else if (FULL) {
+                        scripted_turn(c, P, k);
+                    }
+                }
+                field_update<W, FULL>(c, P);
+                if (c.lane == 0) c.h->frame += 1;
+                c.t.sync();
+            }
+        }
+        if (flags & KF_OBS_AFTER)
+            for (int a = 0; a < A; ++a) nn_turn_begin<W, FULL>(c, P, a, obs_env ? obs_env + (size_t)a * SL : nullptr);
+    }
+    stage_out(P, state, env0, n_here);
+}
+
+/* mode 0: Model(...) + createBot*K + Model.initialize (model.py:51,154-162,90-94; field.py:57-67)
+ * mode 1: Model.resetModel -> Field.reset (field.py:69-83)      mode 2: Model.resetBots (bot.py:125-164) */
+template <int W, bool FULL>
+__global__ void __launch_bounds__(128)
+k_init(const __grid_constant__ DevParams P, uint8_t* __restrict__ state, const uint8_t* __restrict__ mask, int mode) {
+    const int tiles = blockDim.x / W;
+    const int env0 = blockIdx.x * tiles;
+    const int n_here = min(tiles, P.n_envs - env0);
+    stage_in(P, state, env0, n_here, mode == 0);
+    const int tile_id = threadIdx.x / W;
+    if (tile_id < n_here && (mask == nullptr || mode == 0 || mask[env0 + tile_id])) {
+        Ctx<W> c(cg::tiled_partition<W>(cg::this_thread_block()));
+        bind_ctx(c, P, tile_id, tiles, env0 + tile_id);
+        const int K = P.L.n_players;
+        if (mode == 0 || mode == 1) {
+            if (mode == 1) { /* clear pools cooperatively: fresh lists and hash tables */
+                for (int i = c.lane; i < P.L.pellet_cap; i += W) c.pel[i] = 0;
+                AgarFatPellet zf = {};
+                for (int i = c.lane; i < P.L.fat_cap; i += W) c.fat[i] = zf;
+                AgarMote zm = {};
+                for (int i = c.lane; i < P.L.blob_cap; i += W) c.blob[i] = zm;
+                for (int i = c.lane; i < P.L.virus_cap; i += W) c.vir[i] = zm;
+                c.t.sync();
+            }
+            if (c.lane == 0) {
+                if (mode == 0) {
+                    for (int k = 0; k < K; ++k) {
+                        AgarPlayer* p = &c.pl[k];
+                        p->alive = 1;
+                        p->cmd_x = p->cmd_y = -1;
+                        p->bot.type = P.cfg.bot_type[k];
+                    }
+                } else {
+                    c.h->n_events = 0;
+                    c.h->n_pellets = c.h->n_fat = c.h->n_blobs = c.h->n_viruses = 0;
+                    c.h->n_dead = 0;
+                    for (int i = 0; i < AGAR_MAX_PLAYERS; ++i) c.h->dead_order[i] = 0;
+                    for (int k = 0; k < K; ++k)
+                        for (int i = 0; i < c.pl[k].n_cells; ++i) CELLP(c, P, k, i)->flags &= ~AGAR_CF_INHASH;
+                    c.h->frame = 0;
+                }
+                c.h->event_hash = 0xCBF29CE484222325ULL;
+                for (int k = 0; k < K; ++k) initialize_player(c, P, k);
+            }
+            c.t.sync();
+            spawn_pellets(c, P);
+            if (c.lane == 0) {
+                if (P.cfg.virus_enabled) spawn_viruses(c, P);
+                if (c.h->n_dead) spawn_players(c, P);
+            }
+            c.t.sync();
+        }
+        if (mode == 0 || mode == 2) {
+            if (c.lane == 0)
+                for (int k = 0; k < K; ++k) bot_reset(c, P, k);
+            const int nh = P.L.n_agents * P.L.n_hist * P.L.grid_squares * P.L.grid_squares;
+            for (int i = c.lane; i < nh; i += W) c.hist[i] = 0.f;
+            c.t.sync();
+        }
+    }
+    stage_out(P, state, env0, n_here);
+}
+
+/* agar_get: one thread per (env, agent) or per env, straight from HBM */
+__global__ void k_get(const __grid_constant__ DevParams P, const uint8_t* __restrict__ state, int which, void* out) {
+    const int A = P.L.n_agents;
+    const int per_env = (which == AGAR_GET_OVERFLOW || which == AGAR_GET_EVENT_HASH);
+    const int n = per_env ? P.n_envs : P.n_envs * A;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int env = per_env ? i : i / A, a = per_env ? 0 : i - env * A;
+    const uint8_t* rec = state + (size_t)env * P.L.record_bytes;
+    const AgarEnvHeader* h = (const AgarEnvHeader*)(rec + P.L.off_header);
+    const AgarPlayer* p = (const AgarPlayer*)(rec + P.L.off_players) + a;
+    const AgarCell* cells = (const AgarCell*)(rec + P.L.off_cells) + (size_t)a * P.L.cell_cap;
+    switch (which) {
+    case AGAR_GET_REWARD: ((float*)out)[i] = (float)p->bot.last_reward; break;
+    case AGAR_GET_DONE: ((uint8_t*)out)[i] = (uint8_t)p->bot.exp_done; break;
+    case AGAR_GET_VALID: ((uint8_t*)out)[i] = (uint8_t)p->bot.exp_valid; break;
+    case AGAR_GET_NEED_ACTION: ((uint8_t*)out)[i] = (uint8_t)p->bot.need_action; break;
+    case AGAR_GET_MASS: {
+        int nc = p->n_cells;
+        ((float*)out)[i] = nc ? (float)np_sum([&](int j) { return cells[j].mass; }, nc) : 0.f;
+        break;
+    }
+    case AGAR_GET_FOV: ((float*)out)[i] = (float)p->fov_size; break;
+    case AGAR_GET_NCELLS: ((int32_t*)out)[i] = p->n_cells; break;
+    case AGAR_GET_ALIVE: ((uint8_t*)out)[i] = (uint8_t)p->alive; break;
+    case AGAR_GET_STATS: {
+        double* o = (double*)out + (size_t)i * 4;
+        o[0] = p->bot.stat_mass_sum, o[1] = p->bot.stat_mass_max, o[2] = p->bot.stat_frames, o[3] = p->bot.stat_deaths;
+        break;
+    }
+    case AGAR_GET_OVERFLOW: ((uint32_t*)out)[i] = h->overflow; break;
+    case AGAR_GET_EVENT_HASH: ((uint64_t*)out)[i] = h->event_hash; break;
+    }
+}
+
+/* ------------------------------------------------------------------ host side */
+struct AgarEnv {
+    AgarConfig cfg;
+    AgarLayout L;
+    DevParams P;
+    uint8_t* state;
+    double* deg_tab;
+    int n_envs, device, W, full, threads, tiles;
+    size_t smem_bytes;
+    int64_t launches;
+    char err[256];
+    /* step_host staging */
+    float *d_actions, *d_obs, *d_reward;
+    uint8_t* d_done;
+};
+static char g_create_err[256] = "";
+
+static int fail(AgarEnv* e, int code, const char* fmt, const char* detail) {
+    char* dst = e ? e->err : g_create_err;
+    snprintf(dst, 256, fmt, detail);
+    return code;
+}
+#define CU(call)                                                                 \
+    do {                                                                         \
+        cudaError_t _e = (call);                                                 \
+        if (_e != cudaSuccess) return fail(env, AGAR_E_CUDA, "CUDA error: %s", cudaGetErrorString(_e)); \
+    } while (0)
+
+extern "C" int agar_layout_for_config(const AgarConfig* cfg, AgarLayout* out) {
+    if (!cfg || !out) return AGAR_E_INVALID;
+    return agar_layout_compute(cfg, out);
+}
+
+static bool config_is_simple(const AgarConfig& c, const AgarLayout& L) {
+    return c.n_players == 1 && c.bot_type[0] == AGAR_BOT_NN && !c.virus_enabled && !c.enable_split && !c.enable_eject &&
+           L.cell_cap == 1 && !c.self_grid && !c.wall_grid && !c.enemy_grid && !c.virus_grid && !c.self_grid_lf &&
+           !c.self_grid_slf && !c.enemy_grid_lf && !c.enemy_grid_slf && !c.use_last_action && !c.use_second_last_action &&
+           !c.use_last_fovsize && L.n_hist == 0;
+}
+
+/* pick the launch shape for tile width W; returns false if one record does not fit in shared memory */
+static bool plan_launch(AgarEnv* e, int W) {
+    const size_t budget = 200 * 1024;
+    size_t per_tile = (size_t)e->P.rec_stride + (size_t)e->P.scratch_bytes;
+    int tiles = 128 / W;
+    while (tiles > 1 && per_tile * tiles > budget) tiles >>= 1;
+    if (per_tile * tiles > budget) return false;
+    e->W = W;
+    e->tiles = tiles;
+    e->threads = tiles * W;
+    e->smem_bytes = per_tile * tiles;
+    return true;
+}
+
+template <int W, bool FULL>
+static cudaError_t launch_main_t(AgarEnv* e, const float* actions, float* obs, int n_frames, int n_dec, int flags,
+                                 uint32_t dec_base, cudaStream_t s) {
+    cudaError_t err = cudaFuncSetAttribute(k_main<W, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes);
+    if (err != cudaSuccess) return err;
+    int blocks = (e->n_envs + e->tiles - 1) / e->tiles;
+    k_main<W, FULL><<<blocks, e->threads, e->smem_bytes, s>>>(e->P, e->state, actions, obs, n_frames, n_dec, flags, dec_base);
+    return cudaGetLastError();
+}
+template <int W, bool FULL>
+static cudaError_t launch_init_t(AgarEnv* e, const uint8_t* mask, int mode, cudaStream_t s) {
+    cudaError_t err = cudaFuncSetAttribute(k_init<W, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes);
+    if (err != cudaSuccess) return err;
+    int blocks = (e->n_envs + e->tiles - 1) / e->tiles;
+    k_init<W, FULL><<<blocks, e->threads, e->smem_bytes, s>>>(e->P, e->state, mask, mode);
+    return cudaGetLastError();
+}
+#define DISPATCH(fn, ...)                                                 \
+    (e->full ? (e->W == 32  ? fn<32, true>(__VA_ARGS__)                   \
+                : e->W == 16 ? fn<16, true>(__VA_ARGS__)                  \
+                : e->W == 8  ? fn<8, true>(__VA_ARGS__)                   \
+                             : fn<4, true>(__VA_ARGS__))                  \
+             : (e->W == 32  ? fn<32, false>(__VA_ARGS__)                  \
+                : e->W == 16 ? fn<16, false>(__VA_ARGS__)                 \
+                : e->W == 8  ? fn<8, false>(__VA_ARGS__)                  \
+                : e->W == 4  ? fn<4, false>(__VA_ARGS__)                  \
+                : e->W == 2  ? fn<2, false>(__VA_ARGS__)                  \
+                             : fn<1, false>(__VA_ARGS__)))
+
+static int launch_main(AgarEnv* e, const float* actions, float* obs, int n_frames, int n_dec, int flags, uint32_t dec_base,
+                       void* stream) {
+    AgarEnv* env = e;
+    CU(cudaSetDevice(e->device));
+    cudaError_t err = DISPATCH(launch_main_t, e, actions, obs, n_frames, n_dec, flags, dec_base, (cudaStream_t)stream);
+    if (err != cudaSuccess) return fail(e, AGAR_E_CUDA, "kernel launch failed: %s", cudaGetErrorString(err));
+    e->launches += 1;
+    return AGAR_OK;
+}
+static int launch_init(AgarEnv* e, const uint8_t* mask, int mode, void* stream) {
+    AgarEnv* env = e;
+    CU(cudaSetDevice(e->device));
+    cudaError_t err = DISPATCH(launch_init_t, e, mask, mode, (cudaStream_t)stream);
+    if (err != cudaSuccess) return fail(e, AGAR_E_CUDA, "kernel launch failed: %s", cudaGetErrorString(err));
+    e->launches += 1;
+    return AGAR_OK;
+}
+
+extern "C" int agar_set_tile_width(AgarEnv* e, int W) {
+    if (!e) return AGAR_E_INVALID;
+    bool ok = e->full ? (W == 4 || W == 8 || W == 16 || W == 32) : (W == 1 || W == 2 || W == 4 || W == 8 || W == 16 || W == 32);
+    if (!ok) return fail(e, AGAR_E_INVALID, "unsupported tile width%s", "");
+    if (!plan_launch(e, W)) return fail(e, AGAR_E_NOMEM, "env record does not fit in shared memory%s", "");
+    return AGAR_OK;
+}
+extern "C" int agar_get_tile_width(const AgarEnv* e) { return e ? e->W : 0; }
+
+extern "C" int agar_create(const AgarConfig* cfg, int n_envs, int device, uint64_t seed, uint64_t first_env_id, void* stream,
+                           AgarEnv** out) {
+    AgarEnv* env = nullptr;
+    if (!cfg || !out || n_envs < 1) return fail(nullptr, AGAR_E_INVALID, "bad arguments to agar_create%s", "");
+    AgarLayout L;
+    int rc = agar_layout_compute(cfg, &L);
+    if (rc != AGAR_OK) return fail(nullptr, rc, "config rejected by agar_layout_compute%s", "");
+    if (cfg->grid_squares > 16) return fail(nullptr, AGAR_E_UNSUPPORTED, "grid_squares > 16 not supported yet%s", "");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+        return fail(nullptr, AGAR_E_CUDA, "no such CUDA device%s", "");
+    CU(cudaSetDevice(device));
+    AgarEnv* e = (AgarEnv*)calloc(1, sizeof(AgarEnv));
+    env = e;
+    e->cfg = *cfg;
+    e->L = L;
+    e->n_envs = n_envs;
+    e->device = device;
+    e->full = config_is_simple(*cfg, L) ? 0 : 1;
+    DevParams& P = e->P;
+    memset(&P, 0, sizeof P);
+    P.cfg = *cfg;
+    P.L = L;
+    P.S = L.field_size;
+    P.nb = (int)ceil((double)P.S / AG_BUCKET);
+    P.n_envs = n_envs;
+    P.rec_stride = (int)L.record_bytes + 8;
+    P.full = e->full;
+    int vel_bytes = e->full ? L.n_players * L.cell_cap * 2 * 8 : 0;
+    int obs_bytes = obs_scratch_bytes(L.grid_squares, e->full != 0);
+    P.scratch_bytes = ((vel_bytes > obs_bytes ? vel_bytes : obs_bytes) + 15) / 16 * 16 + 8;
+    double speed_modifier = 1.0 / 30;
+    P.move_speed = 90 * speed_modifier;
+    P.decay_rate = 1 - (0.01 * speed_modifier);
+    P.blob_mass = 18 * 0.8;
+    P.virus_split_mass = 100.0 + 7 * 18 * 0.8;
+    P.start_radius = sqrt(10.0 / M_PI);
+    P.virus_radius = sqrt(100.0 / M_PI);
+    for (int m = 0; m < 4; ++m) P.pellet_r[m] = m ? sqrt((double)m / M_PI) : 0.0;
+    for (int n = 1; n <= 16; ++n) P.pow_n[n] = pow((double)n, 0.32);
+    P.seed = seed;
+    P.first_env = first_env_id;
+    double tab[720];
+    for (int d = 0; d < 360; ++d) {
+        double a = d * (M_PI / 180.0);
+        tab[d] = cos(a), tab[360 + d] = sin(a);
+    }
+    if (cudaMalloc(&e->deg_tab, sizeof tab) != cudaSuccess || cudaMalloc(&e->state, (size_t)n_envs * L.record_bytes) != cudaSuccess) {
+        cudaGetLastError();
+        if (e->deg_tab) cudaFree(e->deg_tab);
+        free(e);
+        return fail(nullptr, AGAR_E_NOMEM, "cudaMalloc of the env state failed%s", "");
+    }
+    CU(cudaMemcpyAsync(e->deg_tab, tab, sizeof tab, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    CU(cudaStreamSynchronize((cudaStream_t)stream)); /* tab is a stack buffer */
+    P.deg_tab = e->deg_tab;
+    int W = e->full ? 32 : (n_envs >= 65536 ? 4 : (n_envs >= 16384 ? 8 : 32));
+    const char* wenv = getenv("AGAR_TILE_W");
+    if (wenv && atoi(wenv) > 0) W = atoi(wenv);
+    if (agar_set_tile_width(e, W) != AGAR_OK && agar_set_tile_width(e, 32) != AGAR_OK) {
+        strncpy(g_create_err, e->err, 255);
+        cudaFree(e->state), cudaFree(e->deg_tab), free(e);
+        return AGAR_E_NOMEM;
+    }
+    rc = launch_init(e, nullptr, 0, stream);
+    if (rc != AGAR_OK) {
+        strncpy(g_create_err, e->err, 255);
+        cudaFree(e->state), cudaFree(e->deg_tab), free(e);
+        return rc;
+    }
+    *out = e;
+    return AGAR_OK;
+}
+extern "C" int agar_destroy(AgarEnv* e) {
+    if (!e) return AGAR_E_INVALID;
+    cudaSetDevice(e->device);
+    cudaFree(e->state);
+    cudaFree(e->deg_tab);
+    if (e->d_actions) cudaFree(e->d_actions);
+    if (e->d_obs) cudaFree(e->d_obs);
+    if (e->d_reward) cudaFree(e->d_reward);
+    if (e->d_done) cudaFree(e->d_done);
+    free(e);
+    return AGAR_OK;
+}
+extern "C" const char* agar_last_error(const AgarEnv* e) { return e ? e->err : g_create_err; }
+extern "C" int agar_get_layout(const AgarEnv* e, AgarLayout* out) {
+    if (!e || !out) return AGAR_E_INVALID;
+    *out = e->L;
+    return AGAR_OK;
+}
+extern "C" int agar_num_envs(const AgarEnv* e) { return e ? e->n_envs : AGAR_E_INVALID; }
+extern "C" int64_t agar_launch_count(const AgarEnv* e) { return e ? e->launches : 0; }
+extern "C" void* agar_state_ptr(const AgarEnv* e) { return e ? e->state : nullptr; }
+
+extern "C" int agar_reset(AgarEnv* e, const uint8_t* env_mask_dev, void* stream) {
+    if (!e) return AGAR_E_INVALID;
+    return launch_init(e, env_mask_dev, 1, stream);
+}
+extern "C" int agar_reset_bots(AgarEnv* e, const uint8_t* env_mask_dev, void* stream) {
+    if (!e) return AGAR_E_INVALID;
+    return launch_init(e, env_mask_dev, 2, stream);
+}
+extern "C" int agar_observe(AgarEnv* e, float* obs_dev, void* stream) {
+    if (!e) return AGAR_E_INVALID;
+    return launch_main(e, nullptr, obs_dev, 0, 0, KF_OBS_AFTER, 0, stream);
+}
+extern "C" int agar_step(AgarEnv* e, const float* actions_dev, int n_frames, void* stream) {
+    if (!e || n_frames < 0) return AGAR_E_INVALID;
+    if (!actions_dev && e->L.n_agents > 0) return fail(e, AGAR_E_INVALID, "actions_dev is NULL%s", "");
+    return launch_main(e, actions_dev, nullptr, n_frames, 1, 0, 0, stream);
+}
+extern "C" int agar_step_observe(AgarEnv* e, const float* actions_dev, int n_frames, float* obs_dev, void* stream) {
+    if (!e || n_frames < 0) return AGAR_E_INVALID;
+    if (!actions_dev && e->L.n_agents > 0) return fail(e, AGAR_E_INVALID, "actions_dev is NULL%s", "");
+    return launch_main(e, actions_dev, obs_dev, n_frames, 1, KF_OBS_AFTER, 0, stream);
+}
+/* n_decisions x (observe -> uniform random action from Philox stream 7 -> n_frames frames), one launch.
+ * The random-action driver of BASELINE config 2; obs_dev (nullable) receives every decision's observation. */
+extern "C" int agar_rollout_random(AgarEnv* e, int n_decisions, int n_frames, uint32_t decision_base, float* obs_dev,
+                                   void* stream) {
+    if (!e || n_decisions < 0 || n_frames < 0) return AGAR_E_INVALID;
+    return launch_main(e, nullptr, obs_dev, n_frames, n_decisions, KF_OBS_BEFORE | KF_RANDOM_ACTIONS, decision_base, stream);
+}
+extern "C" int agar_get(AgarEnv* e, AgarField which, void* out_dev, void* stream) {
+    AgarEnv* env = e;
+    if (!e || !out_dev || (int)which < 0 || (int)which > AGAR_GET_EVENT_HASH) return AGAR_E_INVALID;
+    CU(cudaSetDevice(e->device));
+    int per_env = (which == AGAR_GET_OVERFLOW || which == AGAR_GET_EVENT_HASH);
+    int n = per_env ? e->n_envs : e->n_envs * e->L.n_agents;
+    if (n == 0) return AGAR_OK;
+    k_get<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(e->P, e->state, (int)which, out_dev);
+    CU(cudaGetLastError());
+    e->launches += 1;
+    return AGAR_OK;
+}
+extern "C" int agar_debug_dump(AgarEnv* e, int env_index, void* record_host, size_t bytes, void* stream) {
+    AgarEnv* env = e;
+    if (!e || !record_host || env_index < 0 || env_index >= e->n_envs || bytes != e->L.record_bytes) return AGAR_E_INVALID;
+    CU(cudaSetDevice(e->device));
+    CU(cudaMemcpyAsync(record_host, e->state + (size_t)env_index * e->L.record_bytes, bytes, cudaMemcpyDeviceToHost,
+                       (cudaStream_t)stream));
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    return AGAR_OK;
+}
+extern "C" int agar_debug_load(AgarEnv* e, int env_index, const void* record_host, size_t bytes, void* stream) {
+    AgarEnv* env = e;
+    if (!e || !record_host || env_index < 0 || env_index >= e->n_envs || bytes != e->L.record_bytes) return AGAR_E_INVALID;
+    CU(cudaSetDevice(e->device));
+    CU(cudaMemcpyAsync(e->state + (size_t)env_index * e->L.record_bytes, record_host, bytes, cudaMemcpyHostToDevice,
+                       (cudaStream_t)stream));
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    return AGAR_OK;
+}
+extern "C" int agar_step_host(AgarEnv* e, const float* actions_host, int n_frames, float* obs_host, float* reward_host,
+                              uint8_t* done_host, void* stream) {
+    AgarEnv* env = e;
+    if (!e || !actions_host || n_frames < 0) return AGAR_E_INVALID;
+    CU(cudaSetDevice(e->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t EA = (size_t)e->n_envs * (e->L.n_agents ? e->L.n_agents : 1);
+    if (!e->d_actions) {
+        CU(cudaMalloc(&e->d_actions, EA * 4 * sizeof(float)));
+        CU(cudaMalloc(&e->d_obs, EA * e->L.state_len * sizeof(float)));
+        CU(cudaMalloc(&e->d_reward, EA * sizeof(float)));
+        CU(cudaMalloc(&e->d_done, EA));
+        CU(cudaMemsetAsync(e->d_obs, 0, EA * e->L.state_len * sizeof(float), s));
+    }
+    CU(cudaMemcpyAsync(e->d_actions, actions_host, EA * 4 * sizeof(float), cudaMemcpyHostToDevice, s));
+    int rc = launch_main(e, e->d_actions, e->d_obs, n_frames, 1, KF_OBS_AFTER, 0, s);
+    if (rc != AGAR_OK) return rc;
+    if (obs_host) CU(cudaMemcpyAsync(obs_host, e->d_obs, EA * e->L.state_len * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (reward_host) {
+        rc = agar_get(e, AGAR_GET_REWARD, e->d_reward, s);
+        if (rc != AGAR_OK) return rc;
+        CU(cudaMemcpyAsync(reward_host, e->d_reward, EA * sizeof(float), cudaMemcpyDeviceToHost, s));
+    }
+    if (done_host) {
+        rc = agar_get(e, AGAR_GET_DONE, e->d_done, s);
+        if (rc != AGAR_OK) return rc;
+        CU(cudaMemcpyAsync(done_host, e->d_done, EA, cudaMemcpyDeviceToHost, s));
+    }
+    CU(cudaStreamSynchronize(s));
+    return AGAR_OK;
+}

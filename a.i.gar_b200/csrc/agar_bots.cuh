@@ -1,0 +1,463 @@
+/*
+ * agar_bots.cuh — the agent half of the frame: grid-vision observation, reward / done / frame-skip
+ * bookkeeping, action -> command point, and the scripted (greedy / random) opponents.
+ * Replaces src/model/bot.py (file:line cited per function).  Same execution model as agar_dev.cuh.
+ */
+#pragma once
+#include "agar_dev.cuh"
+
+/* scratch layout used while observing (aliases the velocity scratch of update_players) */
+struct ObsScratch {
+    int* pel_i;       /* [(G+1)^2] integer pellet mass per FOV bucket              */
+    double* mid;      /* [2][G]    gsMidPoint sequences (x then y)                 */
+    double* dsum;     /* FULL: pellet sums incl. float pellets                     */
+    double* own;      /* FULL: biggest own cell mass per bucket (as u64 bit patterns while accumulating) */
+    double* enemy;    /* FULL */
+    double* vir_r;    /* FULL: best virus radius per bucket                        */
+    double* vir_m;    /* FULL: its mass                                            */
+};
+__host__ __device__ inline int obs_scratch_bytes(int G, bool full) {
+    int nb = (G + 1) * (G + 1);
+    int bytes = ((nb * 4 + 7) / 8) * 8 + 2 * G * 8;
+    if (full) bytes += 5 * nb * 8;
+    return bytes;
+}
+DEV ObsScratch obs_scratch(uint8_t* base, int G, bool full) {
+    ObsScratch s;
+    int nb = (G + 1) * (G + 1);
+    s.pel_i = (int*)base;
+    base += ((nb * 4 + 7) / 8) * 8;
+    s.mid = (double*)base;
+    base += 2 * G * 8;
+    s.dsum = s.own = s.enemy = s.vir_r = s.vir_m = nullptr;
+    if (full) {
+        s.dsum = (double*)base;
+        s.own = s.dsum + nb;
+        s.enemy = s.own + nb;
+        s.vir_r = s.enemy + nb;
+        s.vir_m = s.vir_r + nb;
+    }
+    return s;
+}
+
+/* spatialHashTable.py:91-108 getIdsForAreaFloatingPoint: calls f(id) once per distinct bucket of the object */
+template <class F>
+DEV void for_each_fov_bucket(double ox, double oy, double radius, double left, double top, double fov, double gs,
+                             int cols, F f) {
+    double px = ox - left, py = oy - top;
+    double cl = py_max0(px - radius), ct = py_max0(py - radius);
+    double bl = cl - fmod(cl, gs), bt = ct - fmod(ct, gs);
+    double lx = (px + radius < fov - 1) ? px + radius : fov - 1;
+    double ly = (py + radius < fov - 1) ? py + radius : fov - 1;
+    int last_col = -1;
+    for (double x = bl; x <= lx; x += gs) {
+        int col = (int)(x / gs);
+        if (col == last_col) continue; /* ids is a set; columns are non-decreasing in x */
+        last_col = col;
+        int last_row = -1;
+        for (double y = bt; y <= ly; y += gs) {
+            int row = (int)(y / gs);
+            if (row == last_row) continue;
+            last_row = row;
+            f(col + row * cols);
+        }
+    }
+}
+
+/* cooperative; bot.py:326-497 + :302-323 + :272-299.  obs: this agent's row of the caller's buffer or nullptr. */
+template <int W, bool FULL>
+DEV void observe_agent(Ctx<W>& c, const DevParams& P, int k, int agent, float* obs) {
+    const AgarConfig& cf = P.cfg;
+    AgarPlayer* p = &c.pl[k];
+    const int G = P.L.grid_squares, GG = G * G;
+    const double S = (double)P.S;
+    if (c.lane == 0) update_fov(c, P, k);
+    c.t.sync();
+    const double fov = p->fov_size, fx = p->fov_x, fy = p->fov_y;
+    const double left = fx - fov / 2, top = fy - fov / 2;
+    const double gs = fov / G;
+    const int cols = cf.obs_mode == AGAR_OBS_CANONICAL ? G : (int)ceil(fov / gs); /* spatialHashTable.py:19 */
+    const int nbk = cols * cols;
+    ObsScratch sc = obs_scratch(c.scratch, G, FULL);
+    for (int i = c.lane; i < nbk; i += W) {
+        sc.pel_i[i] = 0;
+        if (FULL) {
+            ((unsigned long long*)sc.own)[i] = 0ull;
+            ((unsigned long long*)sc.enemy)[i] = 0ull;
+            sc.vir_r[i] = 0.0;
+            sc.vir_m[i] = 0.0;
+        }
+    }
+    if (c.lane == 0) { /* gsMidPoint sequences: mid += gsSize, accumulated exactly like the reference loop */
+        double mx = left + gs / 2, my = top + gs / 2;
+        for (int i = 0; i < G; ++i) {
+            sc.mid[i] = mx;
+            sc.mid[G + i] = my;
+            mx += gs;
+            my += gs;
+        }
+    }
+    c.t.sync();
+    const Rect ra = rect_of(P.S, fx, fy, fov / 2);
+    /* integer pellets (field.getPelletsInFov -> insertAllFloatingPointObjects): integer adds commute */
+    for (int s = c.lane; s < P.L.pellet_cap; s += W) {
+        uint32_t pk = c.pel[s];
+        if (!pk) continue;
+        int px = AGAR_PELLET_X(pk), py = AGAR_PELLET_Y(pk), pm = AGAR_PELLET_M(pk);
+        double pr = P.pellet_r[pm & 3];
+        if (!rect_hit(ra, pellet_rect(px, py)) || !in_fov((double)px, (double)py, pr, fx, fy, fov)) continue;
+        for_each_fov_bucket((double)px, (double)py, pr, left, top, fov, gs, cols,
+                            [&](int id) { atomicAdd(&sc.pel_i[id], pm); });
+    }
+    if (FULL) {
+        /* player cells: max commutes; positive doubles order like their bit patterns */
+        const int K = P.L.n_players, cap = P.L.cell_cap;
+        for (int idx = c.lane; idx < K * cap; idx += W) {
+            int k2 = idx / cap, j = idx - k2 * cap;
+            if (j >= c.pl[k2].n_cells) continue;
+            const AgarCell* o = CELLP(c, P, k2, j);
+            if (k2 == k) { /* own cells: no hash lookup (bot.py:344) */
+                if (!in_fov(o->x, o->y, o->radius, fx, fy, fov)) continue;
+            } else { /* enemies come through the player hash table (field.py:437-439) */
+                if (!(o->flags & AGAR_CF_INHASH) || !rect_hit(ra, rect_of(P.S, o->x, o->y, o->radius)) ||
+                    !in_fov(o->x, o->y, o->radius, fx, fy, fov))
+                    continue;
+            }
+            unsigned long long* grid = (unsigned long long*)(k2 == k ? sc.own : sc.enemy);
+            unsigned long long bits = (unsigned long long)__double_as_longlong(o->mass);
+            for_each_fov_bucket(o->x, o->y, o->radius, left, top, fov, gs, cols,
+                                [&](int id) { atomicMax(&grid[id], bits); });
+        }
+    }
+    c.t.sync();
+    if (FULL) {
+        for (int i = c.lane; i < nbk; i += W) sc.dsum[i] = (double)sc.pel_i[i];
+        c.t.sync();
+        if (c.lane == 0) {
+            /* float pellets are added after the integer ones, in slot order (canonical candidate order) */
+            if (c.h->n_fat)
+                for (int s = 0; s < P.L.fat_cap; ++s) {
+                    const AgarFatPellet* f = &c.fat[s];
+                    if (f->mass == 0) continue;
+                    if (!rect_hit(ra, rect_of(P.S, f->x, f->y, f->radius)) || !in_fov(f->x, f->y, f->radius, fx, fy, fov))
+                        continue;
+                    double fm = f->mass;
+                    for_each_fov_bucket(f->x, f->y, f->radius, left, top, fov, gs, cols,
+                                        [&](int id) { sc.dsum[id] = sc.dsum[id] + fm; });
+                }
+            if (cf.virus_enabled) /* mass of the first virus with the largest radius (bot.py:436-441) */
+                for (int v = 0; v < c.h->n_viruses; ++v) {
+                    const AgarMote* o = &c.vir[v];
+                    if (!(o->aux & AGAR_CF_INHASH) || !rect_hit(ra, rect_of(P.S, o->x, o->y, o->radius)) ||
+                        !in_fov(o->x, o->y, o->radius, fx, fy, fov))
+                        continue;
+                    double orr = o->radius, om = o->mass;
+                    for_each_fov_bucket(o->x, o->y, o->radius, left, top, fov, gs, cols, [&](int id) {
+                        if (orr > sc.vir_r[id]) sc.vir_r[id] = orr, sc.vir_m[id] = om;
+                    });
+                }
+        }
+        c.t.sync();
+    }
+    /* read the G x G squares (bucket index uses G, not cols: the reference's shear when cols == G + 1) */
+    float* hist = (FULL && P.L.n_hist) ? c.hist + (size_t)agent * P.L.n_hist * GG : nullptr;
+    for (int idx = c.lane; idx < GG; idx += W) {
+        int cc = idx / G, r = idx - cc * G;
+        double midx = sc.mid[r], midy = sc.mid[G + cc];
+        bool inside = !(midx + gs / 2 < 0 || midx - gs / 2 > S || midy + gs / 2 < 0 || midy - gs / 2 > S);
+        double v_pel = 0, v_own = 0, v_enemy = 0, v_vir = 0;
+        if (inside) {
+            v_pel = FULL ? sc.dsum[idx] : (double)sc.pel_i[idx];
+            if (FULL) {
+                v_own = sc.own[idx];     /* 0 bits == 0.0: empty bucket */
+                v_enemy = sc.enemy[idx];
+                v_vir = sc.vir_m[idx];
+            }
+        }
+        int ch = 0;
+        if (cf.pellet_grid) {
+            if (obs) obs[ch * GG + idx] = (float)v_pel;
+            ++ch;
+        }
+        if (FULL) {
+            if (cf.self_grid) {
+                if (obs) obs[ch * GG + idx] = (float)v_own;
+                ++ch;
+            }
+            if (cf.wall_grid) { /* bot.py:443-450 */
+                double lb = py_minS(S, py_max0(midx - gs / 2)), tb = py_minS(S, py_max0(midy - gs / 2));
+                double rb = py_max0(py_minS(S, midx + gs / 2)), bb = py_max0(py_minS(S, midy + gs / 2));
+                double free_area = (rb - lb) * (bb - tb);
+                double w = agar_round_dec(1 - (free_area / (gs * gs)), 1e3);
+                if (obs) obs[ch * GG + idx] = (float)w;
+                ++ch;
+            }
+            if (cf.enemy_grid) {
+                if (obs) obs[ch * GG + idx] = (float)v_enemy;
+                ++ch;
+            }
+            if (cf.virus_grid) {
+                if (obs) obs[ch * GG + idx] = (float)v_vir;
+                ++ch;
+            }
+            if (cf.self_grid_slf) {
+                if (obs) obs[ch * GG + idx] = hist[1 * GG + idx];
+                hist[1 * GG + idx] = hist[0 * GG + idx];
+                ++ch;
+            }
+            if (cf.self_grid_lf) {
+                if (obs) obs[ch * GG + idx] = hist[0 * GG + idx];
+                hist[0 * GG + idx] = (float)v_own;
+                ++ch;
+            }
+            if (cf.enemy_grid_slf) {
+                if (obs) obs[ch * GG + idx] = hist[3 * GG + idx];
+                hist[3 * GG + idx] = hist[2 * GG + idx];
+                ++ch;
+            }
+            if (cf.enemy_grid_lf) {
+                if (obs) obs[ch * GG + idx] = hist[2 * GG + idx];
+                hist[2 * GG + idx] = (float)v_enemy;
+                ++ch;
+            }
+        }
+    }
+    if (c.lane == 0) { /* getAdditionalFeatures bot.py:302-323 */
+        AgarBot* B = &p->bot;
+        int n = GG * P.L.n_grids;
+        if (cf.use_last_fovsize) {
+            B->last_fov_size_feat = B->fov_size_feat;
+            if (obs) obs[n] = (float)B->last_fov_size_feat;
+            ++n;
+        }
+        if (cf.use_fovsize) {
+            B->fov_size_feat = p->fov_size;
+            if (obs) obs[n] = (float)B->fov_size_feat;
+            ++n;
+        }
+        if (cf.use_totalmass) {
+            if (obs) obs[n] = (float)total_mass(c, P, k);
+            ++n;
+        }
+        if (cf.use_last_action)
+            for (int i = 0; i < 4; ++i, ++n)
+                if (obs) obs[n] = (float)(B->has_action ? B->cur_action[i] : 0.0);
+        if (cf.use_second_last_action)
+            for (int i = 0; i < 4; ++i, ++n)
+                if (obs) obs[n] = (float)(B->has_last_action ? B->last_action[i] : 0.0);
+    }
+    c.t.sync();
+}
+
+/* lane 0; getReward bot.py:654-667 */
+template <int W>
+DEV double bot_reward(const Ctx<W>& c, const DevParams& P, int k) {
+    const AgarConfig& cf = P.cfg;
+    const AgarPlayer* p = &c.pl[k];
+    if (cf.mass_as_reward) return p->alive ? total_mass(c, P, k) - cf.reward_term : cf.death_term - cf.reward_term;
+    double reward;
+    if (!p->alive)
+        reward = -1 * p->bot.last_mass * cf.death_factor + cf.death_term;
+    else
+        reward = total_mass(c, P, k) - p->bot.last_mass;
+    return reward * cf.reward_scale - cf.reward_term;
+}
+/* lane 0; set_command_point bot.py:550-577 + Player.setCommands */
+template <int W>
+DEV void set_command_point(Ctx<W>& c, const DevParams& P, int k, double a0, double a1, double a2, double a3, int len) {
+    AgarPlayer* p = &c.pl[k];
+    update_fov(c, P, k);
+    int x = (int)p->fov_x, y = (int)p->fov_y;
+    int left = x - (int)(p->fov_size / 2), top = y - (int)(p->fov_size / 2);
+    int size = (int)p->fov_size;
+    p->cmd_x = left + a0 * size;
+    p->cmd_y = top + a1 * size;
+    int split = 0, eject = 0;
+    if (len == 3)
+        split = a2 > 0.5;
+    else if (len == 4) {
+        split = a2 > 0.5;
+        eject = a3 > 0.5;
+    }
+    p->do_split = split;
+    p->do_eject = eject;
+}
+
+/* cooperative; first half of move_NN (bot.py:195-217) + makeMove :253 */
+template <int W, bool FULL>
+DEV void nn_turn_begin(Ctx<W>& c, const DevParams& P, int k, float* obs) {
+    AgarPlayer* p = &c.pl[k];
+    AgarBot* B = &p->bot;
+    int do_obs = 0;
+    if (c.lane == 0 && !B->turn_begun) {
+        double tm = total_mass(c, P, k);
+        B->stat_mass_sum += tm;
+        if (tm > B->stat_mass_max) B->stat_mass_max = tm;
+        B->stat_frames += 1;
+        B->skipping = 0;
+        B->need_action = B->exp_valid = B->exp_done = 0;
+        if (B->has_action) {
+            if (B->has_last_mass && B->last_mass != 0) B->cum_reward += bot_reward(c, P, k);
+            B->last_reward = B->cum_reward;
+            if (B->skip_frames > 0) {
+                B->skip_frames -= 1;
+                if (p->alive) B->skipping = 1;
+            }
+        }
+        if (!B->skipping) {
+            if (B->has_old_state) {
+                B->time += 1;
+                B->exp_valid = 1;
+                B->exp_done = !p->alive;
+            }
+            B->need_action = p->alive;
+            do_obs = p->alive;
+        }
+        B->turn_begun = 1;
+    }
+    do_obs = c.t.shfl(do_obs, 0);
+    if (do_obs) observe_agent<W, FULL>(c, P, k, k, obs);
+}
+/* lane 0; second half of move_NN (bot.py:223-232) + tail of makeMove (:256-270) */
+template <int W>
+DEV void nn_turn_end(Ctx<W>& c, const DevParams& P, int k, const float* action) {
+    AgarPlayer* p = &c.pl[k];
+    AgarBot* B = &p->bot;
+    if (B->need_action) {
+        B->cum_reward = 0;
+        B->skip_frames = P.cfg.frame_skip;
+        B->has_old_state = 1;
+        for (int i = 0; i < 4; ++i) B->last_action[i] = B->cur_action[i];
+        B->has_last_action = B->has_action;
+        for (int i = 0; i < 4; ++i) B->cur_action[i] = i < P.L.action_len ? (double)action[i] : 0.0;
+        B->has_action = 1;
+    }
+    if (!B->skipping && p->alive) {
+        B->last_mass = total_mass(c, P, k);
+        B->has_last_mass = 1;
+    }
+    B->turn_begun = 0;
+    if (!p->alive) return;
+    int len = P.L.action_len;
+    double a2 = B->cur_action[2], a3 = B->cur_action[3];
+    if (B->skipping) a2 = a3 = 0, len = 4;
+    set_command_point(c, P, k, B->cur_action[0], B->cur_action[1], a2, a3, len);
+}
+
+/* cooperative; make_greedy_bot_move bot.py:579-633 / make_random_bot_move :243-249 */
+template <int W>
+DEV void scripted_turn(Ctx<W>& c, const DevParams& P, int k) {
+    AgarPlayer* p = &c.pl[k];
+    AgarBot* B = &p->bot;
+    if (c.lane == 0) {
+        double tm = total_mass(c, P, k);
+        B->stat_mass_sum += tm;
+        if (tm > B->stat_mass_max) B->stat_mass_max = tm;
+        B->stat_frames += 1;
+        if (p->alive) update_fov(c, P, k);
+    }
+    c.t.sync();
+    if (!p->alive) return; /* uniform: nothing below changes alive */
+    if (B->type == AGAR_BOT_GREEDY) {
+        const double fx = p->fov_x, fy = p->fov_y, fov = p->fov_size;
+        int big = 0;
+        const AgarCell* base = CELLP(c, P, k, 0);
+        for (int i = 1; i < p->n_cells; ++i)
+            if (base[i].mass > base[big].mass) big = i;
+        const double bxx = base[big].x, byy = base[big].y, bm = base[big].mass;
+        const Rect ra = rect_of(P.S, fx, fy, fov / 2);
+        /* argmax of mass / d^2 with first-max-wins in canonical order: order index = position in the candidate list */
+        double best = -1.0, bestx = 0, besty = 0;
+        int best_ord = 0x7fffffff;
+        auto consider = [&](double ox, double oy, double om, int ord) {
+            double d2 = (ox - bxx) * (ox - bxx) + (oy - byy) * (oy - byy);
+            double key = om / (d2 != 0 ? d2 : 1);
+            if (key > best || (key == best && ord < best_ord)) best = key, bestx = ox, besty = oy, best_ord = ord;
+        };
+        int ord0 = 0;
+        for (int s = c.lane; s < P.L.pellet_cap; s += W) {
+            uint32_t pk = c.pel[s];
+            if (!pk) continue;
+            int px = AGAR_PELLET_X(pk), py = AGAR_PELLET_Y(pk), pm = AGAR_PELLET_M(pk);
+            double pr = P.pellet_r[pm & 3];
+            if (!rect_hit(ra, pellet_rect(px, py)) || !in_fov((double)px, (double)py, pr, fx, fy, fov)) continue;
+            consider((double)px, (double)py, (double)pm, ord0 + s);
+        }
+        ord0 += P.L.pellet_cap;
+        for (int s = c.lane; s < P.L.fat_cap; s += W) {
+            const AgarFatPellet* f = &c.fat[s];
+            if (f->mass == 0) continue;
+            if (!rect_hit(ra, rect_of(P.S, f->x, f->y, f->radius)) || !in_fov(f->x, f->y, f->radius, fx, fy, fov)) continue;
+            consider(f->x, f->y, f->mass, ord0 + s);
+        }
+        ord0 += P.L.fat_cap;
+        const int K = P.L.n_players, cap = P.L.cell_cap;
+        for (int idx = c.lane; idx < K * cap; idx += W) {
+            int k2 = idx / cap, j = idx - k2 * cap;
+            if (k2 == k || j >= c.pl[k2].n_cells) continue;
+            const AgarCell* o = CELLP(c, P, k2, j);
+            if (!(o->flags & AGAR_CF_INHASH) || !rect_hit(ra, rect_of(P.S, o->x, o->y, o->radius)) ||
+                !in_fov(o->x, o->y, o->radius, fx, fy, fov))
+                continue;
+            if (bm > 1.25 * o->mass) consider(o->x, o->y, o->mass, ord0 + idx);
+        }
+        ord0 += K * cap;
+        if (P.cfg.virus_enabled)
+            for (int v = c.lane; v < c.h->n_viruses; v += W) {
+                const AgarMote* o = &c.vir[v];
+                if (!(o->aux & AGAR_CF_INHASH) || !rect_hit(ra, rect_of(P.S, o->x, o->y, o->radius)) ||
+                    !in_fov(o->x, o->y, o->radius, fx, fy, fov))
+                    continue;
+                if (bm > 1.25 * o->mass) consider(o->x, o->y, o->mass, ord0 + v);
+            }
+        /* tile argmax (key desc, order asc) */
+        for (int off = W / 2; off > 0; off >>= 1) {
+            double ob = c.t.shfl_xor(best, off), ox = c.t.shfl_xor(bestx, off), oy = c.t.shfl_xor(besty, off);
+            int oo = c.t.shfl_xor(best_ord, off);
+            if (ob > best || (ob == best && oo < best_ord)) best = ob, bestx = ox, besty = oy, best_ord = oo;
+        }
+        if (c.lane == 0) {
+            if (best_ord != 0x7fffffff) { /* getRelativeCellPos bot.py:16-20: relative to the FLOAT fov size */
+                int x = (int)fx, y = (int)fy;
+                int left = x - (int)(fov / 2), top = y - (int)(fov / 2);
+                B->cur_action[0] = agar_round_dec((bestx - left) / fov, 1e5);
+                B->cur_action[1] = agar_round_dec((besty - top) / fov, 1e5);
+            } else {
+                B->cur_action[0] = draw_random(c, P, 1);
+                B->cur_action[1] = draw_random(c, P, 1);
+            }
+            B->cur_action[2] = B->cur_action[3] = 0;
+        }
+    } else if (c.lane == 0) {
+        if (P.cfg.frame_skip == 0 || B->time % P.cfg.frame_skip == 0) {
+            B->cur_action[0] = draw_random(c, P, 1);
+            B->cur_action[1] = draw_random(c, P, 1);
+            B->cur_action[2] = P.cfg.enable_split ? draw_random(c, P, 1) : 0;
+            B->cur_action[3] = P.cfg.enable_eject ? draw_random(c, P, 1) : 0;
+        }
+        B->time += 1;
+    }
+    if (c.lane == 0) {
+        B->has_action = 1;
+        set_command_point(c, P, k, B->cur_action[0], B->cur_action[1], B->cur_action[2], B->cur_action[3], 4);
+    }
+    c.t.sync();
+}
+
+/* lane 0; Bot.reset bot.py:125-164 (history grids are cleared by the caller cooperatively) */
+template <int W>
+DEV void bot_reset(Ctx<W>& c, const DevParams& P, int k) {
+    AgarBot* B = &c.pl[k].bot;
+    B->has_last_mass = 0, B->last_mass = 0;
+    B->has_old_state = 0;
+    B->skip_frames = 0;
+    B->cum_reward = 0, B->last_reward = 0;
+    B->skipping = 0;
+    B->turn_begun = B->need_action = B->exp_valid = B->exp_done = 0;
+    for (int i = 0; i < 4; ++i) B->cur_action[i] = 0;
+    if (B->type == AGAR_BOT_NN) {
+        B->has_action = 0;
+        B->fov_size_feat = 0, B->last_fov_size_feat = 0;
+    } else
+        B->has_action = 1;
+}

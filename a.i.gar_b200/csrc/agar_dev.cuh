@@ -1,0 +1,1056 @@
+/*
+ * agar_dev.cuh — device side of the B200-native batched agar.io step.
+ *
+ * Execution model: one env per TILE of W lanes (W = 1..32, a cooperative-groups tile of a warp).  The env
+ * record (include/agar_b200.h) is staged from HBM into shared memory by the whole CTA with coalesced 16-byte
+ * accesses, stepped there for every frame of the launch, and written back once.  Inside a tile, lane 0 is
+ * the "scalar processor" that executes the order-dependent parts of the reference exactly as a sequential
+ * program (SEQ sections); the other lanes are the vector assist for the O(pool) loops: the pellet overlap
+ * scan (ballot + ordered eat chain), free-slot search, field-of-view binning, candidate pre-checks.
+ *
+ * All fp64 arithmetic is IEEE basic operations + include/agar_math.h, compiled with -fmad=false, so that
+ * the state is BIT-IDENTICAL to oracle/agar_oracle.c built with -DAGAR_PORTABLE_MATH.
+ *
+ * Every function cites the reference lines it replaces (paths relative to /root/reference/src/model/).
+ */
+#pragma once
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/agar_b200.h"
+#include "../../include/agar_math.h"
+
+namespace cg = cooperative_groups;
+
+#define DEV __device__ __forceinline__
+#define DEVN __device__ __noinline__
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+/* parameters.py:10-35 */
+#define AG_BUCKET 20
+#define AG_MAX_MASS 22500.0
+
+struct DevParams {
+    AgarConfig cfg;
+    AgarLayout L;
+    int S, nb, n_envs, rec_stride; /* rec_stride: bytes between staged records in shared memory */
+    int scratch_bytes, full, pad0, pad1;
+    double move_speed, decay_rate, blob_mass, virus_split_mass, start_radius, virus_radius;
+    double pellet_r[4];
+    double pow_n[17];
+    const double* deg_tab; /* cos(d*pi/180)[360], sin(...)[360] — host libm, exactly the oracle's table */
+    uint64_t seed, first_env;
+};
+
+/* flags of k_main */
+enum { KF_OBS_BEFORE = 1, KF_OBS_AFTER = 2, KF_RANDOM_ACTIONS = 4 };
+
+template <int W>
+struct Ctx {
+    cg::thread_block_tile<W> t;
+    int lane;
+    uint32_t env_id; /* global env id: Philox counter word 2 */
+    uint8_t* rec;
+    AgarEnvHeader* h;
+    AgarPlayer* pl;
+    AgarCell* cells;
+    AgarMote* vir;
+    AgarMote* blob;
+    AgarFatPellet* fat;
+    uint32_t* pel;
+    float* hist;
+    AgarEvent* ev;
+    uint8_t* scratch;
+    __device__ Ctx(cg::thread_block_tile<W> tile) : t(tile) {}
+};
+
+#define CELLP(c, P, k, i) (&(c).cells[(k) * (P).L.cell_cap + (i)])
+
+/* ------------------------------------------------------------------ small exact helpers */
+DEV double py_max0(double v) { return v > 0 ? v : 0.0; }
+DEV double py_minS(double S, double v) { return v < S ? v : S; }
+DEV double clampS(double v, double S) { return py_minS(S, py_max0(v)); }
+DEV double radius_of(double m) { return m > 0 ? sqrt(m / M_PI) : 0.0; } /* cell.py:210-212 */
+
+struct Rect {
+    int x0, x1, y0, y1;
+};
+/* spatialHashTable.py:70-83 getIdsForArea, one axis */
+DEV void axis_range(double p, double radius, int S, int& b0, int& b1) {
+    double cl = py_max0(p - radius);
+    int bucket_left = (int)(cl - fmod(cl, (double)AG_BUCKET));
+    int limit = (int)py_minS((double)S, p + radius + 1);
+    b0 = bucket_left / AG_BUCKET;
+    b1 = limit > bucket_left ? b0 + (limit - bucket_left - 1) / AG_BUCKET : b0 - 1;
+}
+DEV Rect rect_of(int S, double x, double y, double r) {
+    Rect q;
+    axis_range(x, r, S, q.x0, q.x1);
+    axis_range(y, r, S, q.y0, q.y1);
+    return q;
+}
+DEV bool rect_hit(const Rect& a, const Rect& b) {
+    if (a.x1 < a.x0 || a.y1 < a.y0 || b.x1 < b.x0 || b.y1 < b.y0) return false;
+    return a.x0 <= b.x1 && b.x0 <= a.x1 && a.y0 <= b.y1 && b.y0 <= a.y1;
+}
+/* integer pellet at (px, py), radius < 1: its hash rectangle in closed form (tests/test_layout.py proves it
+ * equal to axis_range for every coordinate and mass) */
+DEV Rect pellet_rect(int px, int py) {
+    Rect q;
+    q.x0 = (px > 0 ? px - 1 : 0) / AG_BUCKET, q.x1 = px / AG_BUCKET;
+    q.y0 = (py > 0 ? py - 1 : 0) / AG_BUCKET, q.y1 = py / AG_BUCKET;
+    return q;
+}
+/* cell.py:143-152 */
+DEV bool overlap(double ax, double ay, double am, double ar, double bx, double by, double bm, double br) {
+    double bigx, bigy, bigr, smx, smy;
+    if (am > bm)
+        bigx = ax, bigy = ay, bigr = ar, smx = bx, smy = by;
+    else
+        bigx = bx, bigy = by, bigr = br, smx = ax, smy = ay;
+    double d2 = (bigx - smx) * (bigx - smx) + (bigy - smy) * (bigy - smy);
+    return d2 * 1.1 < bigr * bigr;
+}
+DEV bool in_fov(double x, double y, double r, double fx, double fy, double fov) { /* cell.py:169-177 */
+    double h = fov / 2;
+    double xmin = fx - h, xmax = fx + h, ymin = fy - h, ymax = fy + h;
+    return !(x + r < xmin || x - r > xmax || y + r < ymin || y - r > ymax);
+}
+DEV void grow(AgarCell* c, double food) { /* cell.py:119-121 */
+    double nm = c->mass + food;
+    if (!(nm < AG_MAX_MASS)) nm = AG_MAX_MASS;
+    c->mass = nm;
+    c->radius = radius_of(nm);
+}
+DEV void grow_mote(AgarMote* c, double food) {
+    double nm = c->mass + food;
+    if (!(nm < AG_MAX_MASS)) nm = AG_MAX_MASS;
+    c->mass = nm;
+    c->radius = radius_of(nm);
+}
+DEV double merge_time_for(double factor, double mass) { /* cell.py:154-155 */
+    return factor * (25 + mass * 0.0233) * 30 / 2 / 1;
+}
+
+/* numpy pairwise summation order for n <= 16 (oracle np_sum) */
+template <class F>
+DEV double np_sum(F get, int n) {
+    if (n < 8) {
+        double r = 0.0;
+        for (int i = 0; i < n; ++i) r += get(i);
+        return r;
+    }
+    double r0 = get(0), r1 = get(1), r2 = get(2), r3 = get(3), r4 = get(4), r5 = get(5), r6 = get(6), r7 = get(7);
+    int i = 8;
+    if (n == 16) {
+        r0 += get(8), r1 += get(9), r2 += get(10), r3 += get(11), r4 += get(12), r5 += get(13), r6 += get(14),
+            r7 += get(15);
+        i = 16;
+    }
+    double res = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+    for (; i < n; ++i) res += get(i);
+    return res;
+}
+
+/* ------------------------------------------------------------------ Philox4x32-10 (oracle/philox.py) */
+DEV void philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0, c1 = n1, c2 = n2, c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0, out[1] = c1, out[2] = c2, out[3] = c3;
+}
+/* the draw_* functions are called by lane 0 only (they advance the serial in the record) */
+template <int W>
+DEV void draw_words(Ctx<W>& c, const DevParams& P, int stream, uint32_t out[4]) {
+    uint32_t* serial = stream == 0 ? &c.h->rng_field : &c.h->rng_bot;
+    philox(*serial, (uint32_t)stream, c.env_id, 0, (uint32_t)P.seed, (uint32_t)(P.seed >> 32), out);
+    *serial += 1;
+}
+template <int W>
+DEV int draw_randint(Ctx<W>& c, const DevParams& P, int stream, double lo, double hi) {
+    long long l = (long long)lo, h = (long long)hi; /* numpy truncates float bounds toward zero */
+    uint32_t w[4];
+    draw_words(c, P, stream, w);
+    return (int)(l + (long long)(((unsigned long long)w[0] * (unsigned long long)(h - l)) >> 32));
+}
+template <int W>
+DEV double draw_random(Ctx<W>& c, const DevParams& P, int stream) {
+    uint32_t w[4];
+    draw_words(c, P, stream, w);
+    return ((double)(w[0] >> 5) * 67108864.0 + (double)(w[1] >> 6)) / 9007199254740992.0;
+}
+
+/* lane 0 only */
+template <int W>
+DEV void log_ev(Ctx<W>& c, const DevParams& P, int type, int a, int b, int cc, int d) {
+    int n = c.h->n_events;
+    if (n < P.L.event_cap) {
+        AgarEvent* ev = &c.ev[n];
+        ev->type = type, ev->a = a, ev->b = b, ev->c = cc, ev->d = d;
+    }
+    c.h->n_events = n + 1;
+    uint64_t hh = c.h->event_hash;
+    hh = (hh ^ (uint64_t)(uint32_t)type) * 0x100000001B3ULL;
+    hh = (hh ^ (uint64_t)(uint32_t)a) * 0x100000001B3ULL;
+    hh = (hh ^ (uint64_t)(uint32_t)b) * 0x100000001B3ULL;
+    hh = (hh ^ (uint64_t)(uint32_t)cc) * 0x100000001B3ULL;
+    hh = (hh ^ (uint64_t)(uint32_t)d) * 0x100000001B3ULL;
+    c.h->event_hash = hh;
+}
+
+/* ------------------------------------------------------------------ player helpers (player.py:129-167); any lane */
+template <int W>
+DEV double total_mass(const Ctx<W>& c, const DevParams& P, int k) {
+    int n = c.pl[k].n_cells;
+    if (n == 0) return 0.0;
+    const AgarCell* base = CELLP(c, P, k, 0);
+    return np_sum([&](int i) { return base[i].mass; }, n);
+}
+/* lane 0: getFovPos + getFovSize, caches in the player */
+template <int W>
+DEV void update_fov(Ctx<W>& c, const DevParams& P, int k) {
+    AgarPlayer* p = &c.pl[k];
+    if (!p->alive) return;
+    int n = p->n_cells;
+    const AgarCell* base = CELLP(c, P, k, 0);
+    double tm = total_mass(c, P, k);
+    if (tm != 0) {
+        p->fov_x = np_sum([&](int i) { return base[i].x * base[i].mass; }, n) / tm;
+        p->fov_y = np_sum([&](int i) { return base[i].y * base[i].mass; }, n) / tm;
+        p->fov_valid = 1;
+    }
+    double rmax = base[0].radius;
+    for (int i = 1; i < n; ++i)
+        if (base[i].radius > rmax) rmax = base[i].radius;
+    p->fov_size = agar_pow(rmax, 0.475) * P.pow_n[n] * 35;
+}
+template <int W>
+DEV void cell_remove(Ctx<W>& c, const DevParams& P, int k, int i) {
+    AgarPlayer* p = &c.pl[k];
+    AgarCell* base = CELLP(c, P, k, 0);
+    for (int j = i; j + 1 < p->n_cells; ++j) base[j] = base[j + 1];
+    p->n_cells -= 1;
+    AgarCell z = {};
+    base[p->n_cells] = z;
+}
+template <int W>
+DEV AgarCell* cell_append(Ctx<W>& c, const DevParams& P, int k, double x, double y, double mass) {
+    AgarPlayer* p = &c.pl[k];
+    AgarCell* nc = CELLP(c, P, k, p->n_cells);
+    AgarCell z = {};
+    *nc = z;
+    nc->x = x, nc->y = y, nc->mass = mass, nc->radius = radius_of(mass);
+    nc->uid = c.h->next_uid++;
+    p->n_cells += 1;
+    return nc;
+}
+template <int W>
+DEV void delete_player_cell(Ctx<W>& c, const DevParams& P, int k, int i) { /* field.py:382-388 */
+    cell_remove(c, P, k, i);
+    AgarPlayer* p = &c.pl[k];
+    if (p->n_cells == 0) {
+        c.h->dead_order[c.h->n_dead++] = k;
+        p->alive = 0;
+        p->respawn_time = 1;
+        log_ev(c, P, AGAR_EV_PLAYER_DIED, k, 0, 0, 0);
+        p->bot.stat_deaths += 1;
+    }
+}
+
+/* ------------------------------------------------------------------ momentum / movement (cell.py:96-141) */
+DEV void add_momentum(double S, double x, double y, double px, double py, double orig_radius, double* svx, double* svy,
+                      int32_t* counter) {
+    double cx = py_max0(py_minS(S, px)), cy = py_max0(py_minS(S, py));
+    double cs, sn;
+    agar_dir(cy - y, cx - x, &cs, &sn);
+    double speed = 2 + orig_radius * 0.05;
+    *svx = cs * speed;
+    *svy = sn * speed;
+    *counter = 15;
+}
+DEV void update_momentum(double& svx, double& svy, int32_t& counter) {
+    if (counter == -1) return;
+    if (counter > 0) {
+        counter -= 1;
+        double ratio = (double)counter / 15;
+        if (ratio < 0.1) {
+            svx *= (1 - ratio);
+            svy *= (1 - ratio);
+        }
+    } else {
+        svx = 0, svy = 0;
+        counter = -1;
+    }
+}
+DEV void update_pos(double& x, double& y, double vx, double vy, double& svx, double& svy, int counter, double S) {
+    double xs = vx + svx, ys = vy + svy;
+    x = clampS(x + xs, S);
+    y = clampS(y + ys, S);
+    if ((counter && x == S) || x == 0) svx *= -1;
+    if ((counter && y == S) || y == 0) svy *= -1;
+}
+
+/* ------------------------------------------------------------------ spawning (field.py:262-313) */
+/* lane 0 */
+template <int W>
+DEV bool player_bucket_occupied(const Ctx<W>& c, const DevParams& P, int bx, int by) {
+    for (int k = 0; k < P.L.n_players; ++k)
+        for (int i = 0; i < c.pl[k].n_cells; ++i) {
+            const AgarCell* q = CELLP(c, P, k, i);
+            if (!(q->flags & AGAR_CF_INHASH)) continue;
+            Rect r = rect_of(P.S, q->x, q->y, q->radius);
+            if (r.x1 < r.x0 || r.y1 < r.y0) continue;
+            if (bx >= r.x0 && bx <= r.x1 && by >= r.y0 && by <= r.y1) return true;
+        }
+    return false;
+}
+template <int W>
+DEV void get_spawn_pos(Ctx<W>& c, const DevParams& P, double radius, double& ox, double& oy) { /* :283-301 */
+    int cols = P.nb, total = cols * cols;
+    int b = draw_randint(c, P, 0, 0, total), count = 0;
+    while (count < total && player_bucket_occupied(c, P, b % cols, b / cols)) {
+        b = (b + 1) % total;
+        count++;
+    }
+    if (count == total) {
+        ox = (double)draw_randint(c, P, 0, 0, P.S);
+        oy = (double)draw_randint(c, P, 0, 0, P.S);
+    } else {
+        int x = b % cols;
+        double y = (double)(b - x) / cols;
+        double left = (double)((x - 1) * AG_BUCKET), top = y * AG_BUCKET;
+        ox = (double)draw_randint(c, P, 0, left + radius, left + AG_BUCKET - radius);
+        oy = (double)draw_randint(c, P, 0, top + radius, top + AG_BUCKET - radius);
+    }
+}
+template <int W>
+DEV void initialize_player(Ctx<W>& c, const DevParams& P, int k) { /* :49-55, lane 0 */
+    AgarPlayer* p = &c.pl[k];
+    AgarCell z = {};
+    for (int i = 0; i < P.L.cell_cap; ++i) *CELLP(c, P, k, i) = z;
+    p->n_cells = 0;
+    double x, y;
+    get_spawn_pos(c, P, P.start_radius, x, y);
+    AgarCell* nc = cell_append(c, P, k, x, y, 10.0);
+    p->alive = 1;
+    p->respawn_time = 0;
+    log_ev(c, P, AGAR_EV_SPAWN_PLAYER, k, (int)nc->uid, (int)x, (int)y);
+}
+/* cooperative: every lane of the tile calls it.  field.py:303-313, :20-26 */
+template <int W>
+DEV void spawn_pellets(Ctx<W>& c, const DevParams& P) {
+    int from = 0;
+    const int cap = P.L.pellet_cap;
+    while (true) {
+        bool need = (double)(c.h->n_pellets + c.h->n_fat) < P.L.max_pellets;
+        if (!need) break;
+        int slot = -1;
+        for (int base = from; base < cap; base += W) {
+            int s = base + c.lane;
+            bool fr = s < cap && c.pel[s] == 0;
+            unsigned b = c.t.ballot(fr);
+            if (b) {
+                slot = base + __ffs(b) - 1;
+                break;
+            }
+        }
+        if (slot < 0) break; /* cannot happen: n_pellets < max <= cap */
+        if (c.lane == 0) {
+            int x = draw_randint(c, P, 0, 0, P.S), y = draw_randint(c, P, 0, 0, P.S);
+            int v = draw_randint(c, P, 0, 0, 50);
+            int m = v > 46 ? 50 - v : 1;
+            log_ev(c, P, AGAR_EV_SPAWN_PELLET, slot, x, y, m);
+            c.pel[slot] = AGAR_PELLET_PACK(x, y, m);
+            c.h->n_pellets += 1;
+        }
+        from = slot + 1;
+        c.t.sync();
+    }
+}
+template <int W>
+DEV void spawn_viruses(Ctx<W>& c, const DevParams& P) { /* lane 0; :262-275 */
+    while ((double)c.h->n_viruses < P.L.max_viruses) {
+        if (c.h->n_viruses >= P.L.virus_cap) {
+            c.h->overflow |= AGAR_OVF_VIRUS;
+            break;
+        }
+        double x, y;
+        get_spawn_pos(c, P, P.virus_radius, x, y);
+        double acc = AG_BUCKET - P.virus_radius;
+        x += (double)draw_randint(c, P, 0, (-1) * acc / 2, acc / 2);
+        y += (double)draw_randint(c, P, 0, (-1) * acc / 2, acc / 2);
+        AgarMote* v = &c.vir[c.h->n_viruses];
+        AgarMote z = {};
+        *v = z;
+        v->x = x, v->y = y, v->mass = 100.0, v->radius = radius_of(100.0);
+        log_ev(c, P, AGAR_EV_SPAWN_VIRUS, c.h->n_viruses, (int)x, (int)y, 0);
+        c.h->n_viruses += 1;
+    }
+}
+template <int W>
+DEV void spawn_players(Ctx<W>& c, const DevParams& P) { /* lane 0; :277-281 */
+    int n = c.h->n_dead, w = 0;
+    int order[AGAR_MAX_PLAYERS];
+    for (int i = 0; i < n; ++i) order[i] = c.h->dead_order[i];
+    for (int i = 0; i < n; ++i) {
+        int k = order[i];
+        if (c.pl[k].respawn_time == 0)
+            initialize_player(c, P, k);
+        else
+            c.h->dead_order[w++] = k;
+    }
+    c.h->n_dead = w;
+    for (int i = w; i < n; ++i) c.h->dead_order[i] = 0;
+}
+template <int W, bool FULL>
+DEV void spawn_stuff(Ctx<W>& c, const DevParams& P) { /* cooperative; :256-260 */
+    spawn_pellets(c, P);
+    if (FULL) {
+        if (c.lane == 0) {
+            if (P.cfg.virus_enabled) spawn_viruses(c, P);
+            if (c.h->n_dead) spawn_players(c, P);
+        }
+        c.t.sync();
+    }
+}
+
+/* ------------------------------------------------------------------ Field.update phases */
+template <int W>
+DEV void blob_remove(Ctx<W>& c, int i) {
+    for (int j = i; j + 1 < c.h->n_blobs; ++j) c.blob[j] = c.blob[j + 1];
+    c.h->n_blobs -= 1;
+    AgarMote z = {};
+    c.blob[c.h->n_blobs] = z;
+}
+template <int W>
+DEV void virus_remove(Ctx<W>& c, int i) {
+    for (int j = i; j + 1 < c.h->n_viruses; ++j) c.vir[j] = c.vir[j + 1];
+    c.h->n_viruses -= 1;
+    AgarMote z = {};
+    c.vir[c.h->n_viruses] = z;
+}
+/* cooperative; field.py:94-110 */
+template <int W>
+DEV void update_viruses_blobs(Ctx<W>& c, const DevParams& P) {
+    const double S = (double)P.S;
+    int nv = c.h->n_viruses, nb = c.h->n_blobs;
+    for (int i = c.lane; i < nv; i += W) {
+        AgarMote* v = &c.vir[i];
+        double svx = v->svx, svy = v->svy, x = v->x, y = v->y;
+        int32_t cnt = v->counter;
+        update_momentum(svx, svy, cnt);
+        update_pos(x, y, 0, 0, svx, svy, cnt, S);
+        v->svx = svx, v->svy = svy, v->x = x, v->y = y, v->counter = cnt;
+    }
+    bool any_still = false;
+    for (int i = c.lane; i < nb; i += W) {
+        AgarMote* b = &c.blob[i];
+        if (b->counter == 0) {
+            any_still = true;
+            continue;
+        }
+        double svx = b->svx, svy = b->svy, x = b->x, y = b->y;
+        int32_t cnt = b->counter;
+        update_momentum(svx, svy, cnt);
+        update_pos(x, y, 0, 0, svx, svy, cnt, S);
+        /* a blob whose counter reaches 0 here stays a blob until the next frame; mark it with counter 0 */
+        b->svx = svx, b->svy = svy, b->x = x, b->y = y, b->counter = cnt;
+        if (cnt == 0) b->aux |= 0x80000000u; /* "reached zero this frame" (cleared below) */
+    }
+    c.t.sync();
+    if (nb && c.t.any(any_still)) {
+        if (c.lane == 0) { /* blobs that were already still become float-position pellets, in list order */
+            int i = 0;
+            while (i < c.h->n_blobs) {
+                AgarMote b = c.blob[i];
+                if (b.counter != 0 || (b.aux & 0x80000000u)) {
+                    ++i;
+                    continue;
+                }
+                blob_remove(c, i);
+                int slot = 0;
+                while (slot < P.L.fat_cap && c.fat[slot].mass != 0) ++slot;
+                if (slot == P.L.fat_cap) {
+                    c.h->overflow |= AGAR_OVF_FAT;
+                    continue;
+                }
+                AgarFatPellet* f = &c.fat[slot];
+                f->x = b.x, f->y = b.y, f->mass = b.mass, f->radius = b.radius;
+                c.h->n_fat += 1;
+                log_ev(c, P, AGAR_EV_BLOB_TO_PELLET, slot, 0, 0, 0);
+            }
+        }
+        c.t.sync();
+    }
+    if (nb) {
+        for (int i = c.lane; i < c.h->n_blobs; i += W) c.blob[i].aux &= 0x7fffffffu;
+        c.t.sync();
+    }
+}
+
+/* lane 0: split / eject flag / movement / ejections / collisions of one player.  vel = scratch [cells][2]. */
+template <int W>
+DEVN void player_rare_path(Ctx<W>& c, const DevParams& P, int k, double* vel) {
+    AgarPlayer* p = &c.pl[k];
+    AgarCell* base = CELLP(c, P, k, 0);
+    const double S = (double)P.S;
+    double* vx = vel + (size_t)k * P.L.cell_cap * 2;
+    double* vy = vx + P.L.cell_cap;
+    if (p->do_split) { /* player.py:53-61 */
+        for (int i = 1; i < p->n_cells; ++i) {
+            AgarCell t = base[i];
+            double tvx = vx[i], tvy = vy[i];
+            int j = i - 1;
+            while (j >= 0 && base[j].mass < t.mass) {
+                base[j + 1] = base[j];
+                vx[j + 1] = vx[j], vy[j + 1] = vy[j];
+                --j;
+            }
+            base[j + 1] = t;
+            vx[j + 1] = tvx, vy[j + 1] = tvy;
+        }
+        int n0 = p->n_cells;
+        for (int i = 0; i < n0; ++i) {
+            AgarCell* q = &base[i];
+            if (q->mass > 36 && p->n_cells < 16) { /* cell.py:72-85 */
+                double parent_radius = q->radius;
+                int ni = p->n_cells;
+                AgarCell* nc = cell_append(c, P, k, q->x, q->y, q->mass / 2);
+                vx[ni] = 0, vy[ni] = 0;
+                double cs, sn;
+                agar_dir(p->cmd_y - nc->y, p->cmd_x - nc->x, &cs, &sn);
+                double xp = cs * nc->radius * 4.5 + q->x, yp = sn * nc->radius * 4.5 + q->y;
+                add_momentum(S, nc->x, nc->y, xp, yp, parent_radius, &nc->svx, &nc->svy, &nc->counter);
+                nc->merge_time = merge_time_for(1, nc->mass);
+                q->mass = q->mass / 2;
+                q->radius = radius_of(q->mass);
+                log_ev(c, P, AGAR_EV_SPLIT, k, (int)q->uid, (int)nc->uid, 0);
+            }
+        }
+    }
+    if (p->do_eject) /* player.py:63-68 */
+        for (int i = 0; i < p->n_cells; ++i)
+            if (base[i].mass >= 35) base[i].flags |= AGAR_CF_EJECT;
+    for (int i = 0; i < p->n_cells; ++i) { /* updateCellsMovement */
+        AgarCell* q = &base[i];
+        update_pos(q->x, q->y, vx[i], vy[i], q->svx, q->svy, q->counter, S);
+    }
+    if (p->do_eject) /* field.py:134-146, cell.py:90-94 */
+        for (int i = 0; i < p->n_cells; ++i) {
+            AgarCell* q = &base[i];
+            if (!(q->flags & AGAR_CF_EJECT)) continue;
+            q->mass -= 18;
+            q->flags &= ~AGAR_CF_EJECT;
+            if (c.h->n_blobs >= P.L.blob_cap) {
+                c.h->overflow |= AGAR_OVF_BLOB;
+                continue;
+            }
+            AgarMote* b = &c.blob[c.h->n_blobs];
+            AgarMote z = {};
+            *b = z;
+            b->x = q->x, b->y = q->y, b->mass = P.blob_mass, b->radius = radius_of(P.blob_mass);
+            add_momentum(S, b->x, b->y, p->cmd_x, p->cmd_y, q->radius, &b->svx, &b->svy, &b->counter);
+            b->aux = q->uid;
+            log_ev(c, P, AGAR_EV_EJECT, k, (int)q->uid, c.h->n_blobs, 0);
+            c.h->n_blobs += 1;
+        }
+    /* handlePlayerCollisions field.py:149-181 */
+    for (int i = 0; i < p->n_cells; ++i) {
+        AgarCell* a = &base[i];
+        if (a->counter > 0) continue;
+        for (int j = 0; j < p->n_cells; ++j) {
+            AgarCell* b = &base[j];
+            if (i == j || b->counter > 0 || (a->merge_time <= 0 && b->merge_time <= 0)) continue;
+            double d2 = (a->x - b->x) * (a->x - b->x) + (a->y - b->y) * (a->y - b->y);
+            double dist = sqrt(d2), sum = a->radius + b->radius;
+            if (dist < sum && dist != 0) {
+                log_ev(c, P, AGAR_EV_COLLIDE, k, (int)a->uid, (int)b->uid, 0);
+                AgarCell *big, *sm;
+                if (a->mass > b->mass)
+                    big = a, sm = b;
+                else
+                    big = b, sm = a;
+                double ds = (sum - dist) / dist, q = sm->mass / big->mass;
+                double xs = (big->x - sm->x) * ds, ys = (big->y - sm->y) * ds;
+                double nbx = big->x + xs * q, nby = big->y + ys * q;
+                double nsx = sm->x - xs * (1 - q), nsy = sm->y - ys * (1 - q);
+                big->x = clampS(nbx, S), big->y = clampS(nby, S);
+                sm->x = clampS(nsx, S), sm->y = clampS(nsy, S);
+            }
+        }
+    }
+}
+
+/* per-cell kinematics of one cell: decay, momentum, merge timer, velocity (player.py:43-51; cell.py:47-57,105-130) */
+DEV void cell_kinematics(const DevParams& P, AgarCell* q, double cmd_x, double cmd_y, double& vx, double& vy) {
+    double mass = q->mass, radius = q->radius;
+    if (mass >= 4) {
+        mass = mass * P.decay_rate;
+        radius = radius_of(mass);
+        q->mass = mass, q->radius = radius;
+    }
+    double svx = q->svx, svy = q->svy;
+    int32_t cnt = q->counter;
+    update_momentum(svx, svy, cnt);
+    q->svx = svx, q->svy = svy, q->counter = cnt;
+    double mt = q->merge_time;
+    if (mt > 0) q->merge_time = mt - 1;
+    double xd = cmd_x - q->x, yd = cmd_y - q->y;
+    double h2 = xd * xd + yd * yd, r2 = radius * radius;
+    double sm = (h2 < r2 ? h2 : r2) / r2;
+    double cs, sn;
+    agar_dir(yd, xd, &cs, &sn);
+    double rs = P.move_speed * agar_pow(mass, -0.35);
+    vx = rs * sm * cs;
+    vy = rs * sm * sn;
+}
+
+/* cooperative; field.py:112-132 (updatePlayers + updateHashTables) */
+template <int W, bool FULL>
+DEV void update_players(Ctx<W>& c, const DevParams& P) {
+    const double S = (double)P.S;
+    if (!FULL) { /* K == 1, one cell, no split / eject / virus: everything is lane 0's */
+        if (c.lane == 0) {
+            AgarPlayer* p = &c.pl[0];
+            AgarCell* q = &c.cells[0];
+            double vx, vy;
+            cell_kinematics(P, q, p->cmd_x, p->cmd_y, vx, vy);
+            update_pos(q->x, q->y, vx, vy, q->svx, q->svy, q->counter, S);
+            q->flags |= AGAR_CF_INHASH;
+        }
+        c.t.sync();
+        return;
+    }
+    const int K = P.L.n_players, cap = P.L.cell_cap;
+    double* vel = (double*)c.scratch; /* [K][2][cap] */
+    /* phase A: every live cell of every live player, lane-parallel */
+    for (int idx = c.lane; idx < K * cap; idx += W) {
+        int k = idx / cap, i = idx - k * cap;
+        const AgarPlayer* p = &c.pl[k];
+        if (!p->alive || i >= p->n_cells) continue;
+        double vx, vy;
+        cell_kinematics(P, CELLP(c, P, k, i), p->cmd_x, p->cmd_y, vx, vy);
+        vel[(size_t)k * cap * 2 + i] = vx;
+        vel[(size_t)k * cap * 2 + cap + i] = vy;
+    }
+    c.t.sync();
+    /* phase B: per player, in player order (events and the blob list are ordered by player) */
+    for (int k = 0; k < K; ++k) {
+        AgarPlayer* p = &c.pl[k];
+        if (!p->alive) {
+            if (c.lane == 0) p->respawn_time -= 1;
+            continue;
+        }
+        bool rare = p->do_split || p->do_eject || p->n_cells > 1;
+        if (rare) {
+            if (c.lane == 0) player_rare_path(c, P, k, vel);
+        } else if (c.lane == 0) {
+            AgarCell* q = CELLP(c, P, k, 0);
+            update_pos(q->x, q->y, vel[(size_t)k * cap * 2], vel[(size_t)k * cap * 2 + cap], q->svx, q->svy, q->counter, S);
+        }
+    }
+    c.t.sync();
+    /* updateHashTables: every live cell / virus is (re)inserted */
+    for (int idx = c.lane; idx < K * cap; idx += W) {
+        int k = idx / cap, i = idx - k * cap;
+        if (i < c.pl[k].n_cells) CELLP(c, P, k, i)->flags |= AGAR_CF_INHASH;
+    }
+    for (int i = c.lane; i < c.h->n_viruses; i += W) c.vir[i].aux = AGAR_CF_INHASH;
+    c.t.sync();
+}
+
+/* lane 0; field.py:183-198, :372-380 */
+template <int W>
+DEVN void merge_player_cells_seq(Ctx<W>& c, const DevParams& P, int k) {
+    AgarPlayer* p = &c.pl[k];
+    AgarCell* base = CELLP(c, P, k, 0);
+    uint32_t uid[AGAR_MAX_CELLS];
+    double mass[AGAR_MAX_CELLS];
+    int n = 0;
+    for (int i = 0; i < p->n_cells; ++i)
+        if (base[i].merge_time <= 0) uid[n] = base[i].uid, mass[n] = base[i].mass, ++n;
+    if (n <= 1) return;
+    for (int a = 1; a < n; ++a) {
+        uint32_t tu = uid[a];
+        double tm = mass[a];
+        int j = a - 1;
+        while (j >= 0 && mass[j] < tm) {
+            uid[j + 1] = uid[j], mass[j + 1] = mass[j];
+            --j;
+        }
+        uid[j + 1] = tu, mass[j + 1] = tm;
+    }
+    unsigned alive = (1u << n) - 1;
+    for (int a = 0; a < n; ++a) {
+        if (!(alive >> a & 1)) continue;
+        for (int b = 0; b < n; ++b) {
+            if (!(alive >> b & 1) || b == a) continue;
+            int ia = -1, ib = -1;
+            for (int i = 0; i < p->n_cells; ++i) {
+                if (base[i].uid == uid[a]) ia = i;
+                if (base[i].uid == uid[b]) ib = i;
+            }
+            AgarCell *c1 = &base[ia], *c2 = &base[ib];
+            if (overlap(c1->x, c1->y, c1->mass, c1->radius, c2->x, c2->y, c2->mass, c2->radius)) {
+                bool first_big = c1->mass > c2->mass;
+                AgarCell *cb = first_big ? c1 : c2, *cs = first_big ? c2 : c1;
+                int sm = first_big ? b : a;
+                log_ev(c, P, AGAR_EV_MERGE, k, (int)cb->uid, (int)cs->uid, 0);
+                grow(cb, cs->mass);
+                alive &= ~(1u << sm);
+                delete_player_cell(c, P, k, first_big ? ib : ia);
+                if (!(alive >> a & 1)) break;
+            }
+        }
+    }
+}
+
+/* lane 0; field.py:246-253, :316-325 */
+template <int W>
+DEVN void virus_blob_overlap_seq(Ctx<W>& c, const DevParams& P) {
+    const double S = (double)P.S;
+    for (int vi = 0; vi < c.h->n_viruses; ++vi) {
+        AgarMote* v = &c.vir[vi];
+        Rect rv = rect_of(P.S, v->x, v->y, v->radius);
+        /* candidates are the blobs sharing a bucket with the virus BEFORE it eats; kept as a bitmask walk */
+        int nb0 = c.h->n_blobs;
+        int removed_before = 0;
+        for (int b0 = 0; b0 < nb0; ++b0) {
+            int b = b0 - removed_before;
+            AgarMote* bl = &c.blob[b];
+            /* rect test uses the virus rectangle at the start of its pass (rv) */
+            if (!rect_hit(rv, rect_of(P.S, bl->x, bl->y, bl->radius))) continue;
+            if (!overlap(v->x, v->y, v->mass, v->radius, bl->x, bl->y, bl->mass, bl->radius)) continue;
+            double bx = bl->x, by = bl->y;
+            grow_mote(v, bl->mass);
+            blob_remove(c, b);
+            removed_before += 1;
+            int split = 0;
+            if (v->mass >= P.virus_split_mass) {
+                if (c.h->n_viruses >= P.L.virus_cap)
+                    c.h->overflow |= AGAR_OVF_VIRUS;
+                else {
+                    double ox = 2 * v->x - bx, oy = 2 * v->y - by;
+                    AgarMote* nv = &c.vir[c.h->n_viruses];
+                    AgarMote z = {};
+                    *nv = z;
+                    nv->x = v->x, nv->y = v->y, nv->mass = v->mass / 2, nv->radius = radius_of(nv->mass);
+                    double cs, sn;
+                    agar_dir(oy - nv->y, ox - nv->x, &cs, &sn);
+                    double xp = cs * nv->radius * 4.5 + v->x, yp = sn * nv->radius * 4.5 + v->y;
+                    add_momentum(S, nv->x, nv->y, xp, yp, v->radius, &nv->svx, &nv->svy, &nv->counter);
+                    v->mass = v->mass / 2;
+                    v->radius = radius_of(v->mass);
+                    c.h->n_viruses += 1;
+                    split = 1;
+                }
+            }
+            log_ev(c, P, AGAR_EV_VIRUS_EAT_BLOB, vi, b, split, 0);
+        }
+    }
+}
+
+/* lane 0; field.py:350-370 */
+template <int W>
+DEV void player_cell_ate_virus(Ctx<W>& c, const DevParams& P, int k, int ci) {
+    const double S = (double)P.S;
+    AgarPlayer* p = &c.pl[k];
+    int n_new = 16 - p->n_cells;
+    if (n_new == 0) return;
+    AgarCell* q = CELLP(c, P, k, ci);
+    double distributed = q->mass * 0.6;
+    double per = distributed / n_new;
+    q->merge_time = merge_time_for(0.85, q->mass);
+    grow(q, -1 * per * n_new);
+    for (int j = 0; j < n_new; ++j) {
+        AgarCell* nc = cell_append(c, P, k, q->x, q->y, per);
+        int deg = draw_randint(c, P, 0, 0, 360);
+        double cs = P.deg_tab[deg], sn = P.deg_tab[360 + deg];
+        double xp = cs * q->radius * 12 + q->x, yp = sn * q->radius * 12 + q->y;
+        add_momentum(S, nc->x, nc->y, xp, yp, q->radius, &nc->svx, &nc->svy, &nc->counter);
+        nc->merge_time = merge_time_for(0.8, nc->mass);
+        nc->flags |= AGAR_CF_INHASH;
+    }
+}
+/* lane 0; field.py:225-231, :333-335 */
+template <int W>
+DEVN void player_virus_overlap_seq(Ctx<W>& c, const DevParams& P) {
+    for (int k = 0; k < P.L.n_players; ++k) {
+        AgarPlayer* p = &c.pl[k];
+        if (!p->alive) continue;
+        for (int ci = 0; ci < p->n_cells; ++ci) {
+            AgarCell* q = CELLP(c, P, k, ci);
+            Rect rc = rect_of(P.S, q->x, q->y, q->radius);
+            /* candidate set fixed at the start of the cell's pass: bit v0 of a 64-bit mask over the virus list */
+            unsigned long long cand = 0;
+            int nv0 = c.h->n_viruses;
+            for (int v = 0; v < nv0 && v < 64; ++v)
+                if ((c.vir[v].aux & AGAR_CF_INHASH) &&
+                    rect_hit(rc, rect_of(P.S, c.vir[v].x, c.vir[v].y, c.vir[v].radius)))
+                    cand |= 1ull << v;
+            int removed = 0;
+            for (int v0 = 0; v0 < nv0 && v0 < 64; ++v0) {
+                if (!(cand >> v0 & 1)) continue;
+                int vi = v0 - removed;
+                AgarMote* v = &c.vir[vi];
+                if (overlap(q->x, q->y, q->mass, q->radius, v->x, v->y, v->mass, v->radius) && q->mass > 1.25 * v->mass) {
+                    log_ev(c, P, AGAR_EV_EAT_VIRUS, k, (int)q->uid, vi, 16 - p->n_cells);
+                    grow(q, v->mass * 0.5);
+                    virus_remove(c, vi);
+                    removed += 1;
+                    player_cell_ate_virus(c, P, k, ci);
+                }
+            }
+        }
+    }
+}
+
+/* cooperative: the hot loop.  field.py:207-213 + eatPellet :327-344.  For one cell (k, ci): integer pellets in slot
+ * order, then float ("fat") pellets in slot order; the eat chain is sequential — a pellet is tested against the
+ * cell as grown by every earlier eat — but hits are found 32 pellets at a time with a ballot. */
+template <int W>
+DEV void cell_eats_pellets(Ctx<W>& c, const DevParams& P, int k, int ci, bool fat_too) {
+    AgarCell* q = CELLP(c, P, k, ci);
+    double cx = q->x, cy = q->y, cm = q->mass, cr = q->radius;
+    const Rect rc = rect_of(P.S, cx, cy, cr); /* candidates are fixed before the cell grows */
+    const int cap = P.L.pellet_cap;
+    /* conservative integer window: nothing farther than the largest radius this cell can reach this frame
+     * matters.  Not used for correctness, only the exact tests below are. */
+    for (int base = 0; base < cap; base += W) {
+        int s = base + c.lane;
+        uint32_t pk = s < cap ? c.pel[s] : 0u;
+        int px = AGAR_PELLET_X(pk), py = AGAR_PELLET_Y(pk), pm = AGAR_PELLET_M(pk);
+        bool cand = pk != 0 && rect_hit(rc, pellet_rect(px, py));
+        double pr = P.pellet_r[pm & 3];
+        unsigned done_mask = 0; /* lanes at or below the last eaten one */
+        while (true) {
+            bool hit = cand && overlap(cx, cy, cm, cr, (double)px, (double)py, (double)pm, pr) && cm > 1.25 * (double)pm;
+            unsigned b = c.t.ballot(hit) & ~done_mask;
+            if (!b) break;
+            int l = __ffs(b) - 1;
+            int em = c.t.shfl(pm, l);
+            /* every lane tracks the grown cell identically (grow(): cell.py:119-121) */
+            double nm = cm + (double)em;
+            if (!(nm < AG_MAX_MASS)) nm = AG_MAX_MASS;
+            cm = nm;
+            cr = radius_of(nm);
+            if (c.lane == 0) {
+                log_ev(c, P, AGAR_EV_EAT_PELLET, k, (int)q->uid, base + l, 0);
+                c.pel[base + l] = 0;
+                c.h->n_pellets -= 1;
+            }
+            done_mask |= (l == 31) ? 0xffffffffu : ((2u << l) - 1);
+        }
+    }
+    if (fat_too) {
+        const int fcap = P.L.fat_cap;
+        for (int base = 0; base < fcap; base += W) {
+            int s = base + c.lane;
+            double fx = 0, fy = 0, fm = 0, fr = 0;
+            if (s < fcap) fx = c.fat[s].x, fy = c.fat[s].y, fm = c.fat[s].mass, fr = c.fat[s].radius;
+            bool cand = fm != 0 && rect_hit(rc, rect_of(P.S, fx, fy, fr));
+            unsigned done_mask = 0;
+            while (true) {
+                bool hit = cand && overlap(cx, cy, cm, cr, fx, fy, fm, fr) && cm > 1.25 * fm;
+                unsigned b = c.t.ballot(hit) & ~done_mask;
+                if (!b) break;
+                int l = __ffs(b) - 1;
+                double em = c.t.shfl(fm, l);
+                double nm = cm + em;
+                if (!(nm < AG_MAX_MASS)) nm = AG_MAX_MASS;
+                cm = nm;
+                cr = radius_of(nm);
+                if (c.lane == 0) {
+                    log_ev(c, P, AGAR_EV_EAT_PELLET, k, (int)q->uid, (base + l) | 0x10000, 0);
+                    AgarFatPellet z = {};
+                    c.fat[base + l] = z;
+                    c.h->n_fat -= 1;
+                }
+                done_mask |= (l == 31) ? 0xffffffffu : ((2u << l) - 1);
+            }
+        }
+    }
+    if (c.lane == 0 && cm != q->mass) q->mass = cm, q->radius = cr;
+    c.t.sync();
+}
+
+/* lane 0; field.py:215-222 */
+template <int W>
+DEVN void player_blob_overlap_seq(Ctx<W>& c, const DevParams& P) {
+    for (int k = 0; k < P.L.n_players; ++k) {
+        AgarPlayer* p = &c.pl[k];
+        if (!p->alive) continue;
+        for (int ci = 0; ci < p->n_cells; ++ci) {
+            AgarCell* q = CELLP(c, P, k, ci);
+            Rect rc = rect_of(P.S, q->x, q->y, q->radius);
+            int nb0 = c.h->n_blobs, removed = 0;
+            for (int b0 = 0; b0 < nb0; ++b0) {
+                int bi = b0 - removed;
+                AgarMote* b = &c.blob[bi];
+                if (!rect_hit(rc, rect_of(P.S, b->x, b->y, b->radius))) continue;
+                if (overlap(q->x, q->y, q->mass, q->radius, b->x, b->y, b->mass, b->radius) && b->aux != q->uid &&
+                    q->mass > 1.25 * b->mass) {
+                    log_ev(c, P, AGAR_EV_EAT_BLOB, k, (int)q->uid, bi, (int)b->aux);
+                    grow(q, b->mass);
+                    blob_remove(c, bi);
+                    removed += 1;
+                }
+            }
+        }
+    }
+}
+
+/* lane 0; field.py:233-244, :346-348 */
+template <int W>
+DEVN void player_player_overlap_seq(Ctx<W>& c, const DevParams& P) {
+    const int K = P.L.n_players;
+    for (int k = 0; k < K; ++k) {
+        AgarPlayer* p = &c.pl[k];
+        if (!p->alive) continue;
+        for (int ci = 0; ci < p->n_cells; ++ci) {
+            AgarCell* q = CELLP(c, P, k, ci);
+            uint32_t my_uid = q->uid;
+            Rect rc = rect_of(P.S, q->x, q->y, q->radius);
+            /* candidate snapshot: per enemy player a 16-bit mask over its cell list, taken before any eating;
+             * enemy lists only shrink by this cell's own eating, tracked with `removed` per player */
+            bool eaten = false;
+            for (int k2 = 0; k2 < K && !eaten; ++k2) {
+                if (k2 == k) continue;
+                AgarPlayer* p2 = &c.pl[k2];
+                int n2 = p2->n_cells;
+                unsigned cand = 0;
+                for (int j = 0; j < n2; ++j) {
+                    const AgarCell* o = CELLP(c, P, k2, j);
+                    if ((o->flags & AGAR_CF_INHASH) && rect_hit(rc, rect_of(P.S, o->x, o->y, o->radius))) cand |= 1u << j;
+                }
+                int removed = 0;
+                for (int j0 = 0; j0 < n2; ++j0) {
+                    if (!(cand >> j0 & 1)) continue;
+                    int j = j0 - removed;
+                    AgarCell* o = CELLP(c, P, k2, j);
+                    if (!overlap(q->x, q->y, q->mass, q->radius, o->x, o->y, o->mass, o->radius)) continue;
+                    if (q->mass > 1.25 * o->mass) {
+                        log_ev(c, P, AGAR_EV_EAT_CELL, k, (int)q->uid, k2, (int)o->uid);
+                        grow(q, o->mass);
+                        delete_player_cell(c, P, k2, j);
+                        removed += 1;
+                    } else if (o->mass > 1.25 * q->mass) {
+                        log_ev(c, P, AGAR_EV_EAT_CELL, k2, (int)o->uid, k, (int)my_uid);
+                        grow(o, q->mass);
+                        delete_player_cell(c, P, k, ci);
+                        eaten = true;
+                        break;
+                    }
+                }
+            }
+        }
+    }
+}
+
+/* cooperative pre-checks: does ANY (cell, object) pair satisfy the eat predicate on the current state?  If not,
+ * the sequential pass would change nothing (state only changes through a first hit) and is skipped. */
+template <int W>
+DEV bool any_player_mote_hit(Ctx<W>& c, const DevParams& P, const AgarMote* motes, int n, bool is_virus) {
+    const int K = P.L.n_players, cap = P.L.cell_cap;
+    bool hit = false;
+    if (n > 0)
+        for (int idx = c.lane; idx < K * cap && !hit; idx += W) {
+            int k = idx / cap, i = idx - k * cap;
+            if (!c.pl[k].alive || i >= c.pl[k].n_cells) continue;
+            const AgarCell* q = CELLP(c, P, k, i);
+            for (int v = 0; v < n; ++v) {
+                const AgarMote* m = &motes[v];
+                if (overlap(q->x, q->y, q->mass, q->radius, m->x, m->y, m->mass, m->radius) && q->mass > 1.25 * m->mass &&
+                    (is_virus || m->aux != q->uid)) {
+                    hit = true;
+                    break;
+                }
+            }
+        }
+    return c.t.any(hit);
+}
+template <int W>
+DEV bool any_player_player_hit(Ctx<W>& c, const DevParams& P) {
+    const int K = P.L.n_players, cap = P.L.cell_cap;
+    bool hit = false;
+    for (int idx = c.lane; idx < K * cap && !hit; idx += W) {
+        int k = idx / cap, i = idx - k * cap;
+        if (!c.pl[k].alive || i >= c.pl[k].n_cells) continue;
+        const AgarCell* q = CELLP(c, P, k, i);
+        for (int k2 = k + 1; k2 < K && !hit; ++k2) {
+            int n2 = c.pl[k2].n_cells;
+            for (int j = 0; j < n2; ++j) {
+                const AgarCell* o = CELLP(c, P, k2, j);
+                if (overlap(q->x, q->y, q->mass, q->radius, o->x, o->y, o->mass, o->radius)) {
+                    hit = true;
+                    break;
+                }
+            }
+        }
+    }
+    return c.t.any(hit);
+}
+template <int W>
+DEV bool any_virus_blob_hit(Ctx<W>& c, const DevParams& P) {
+    int nv = c.h->n_viruses, nb = c.h->n_blobs;
+    bool hit = false;
+    for (int idx = c.lane; idx < nv * nb && !hit; idx += W) {
+        const AgarMote *v = &c.vir[idx / nb], *b = &c.blob[idx % nb];
+        if (overlap(v->x, v->y, v->mass, v->radius, b->x, b->y, b->mass, b->radius)) hit = true;
+    }
+    return c.t.any(hit);
+}
+
+/* cooperative; field.py:85-92 */
+template <int W, bool FULL>
+DEV void field_update(Ctx<W>& c, const DevParams& P) {
+    if (FULL) update_viruses_blobs(c, P);
+    update_players<W, FULL>(c, P);
+    if (FULL) {
+        /* mergePlayerCells: only players with >= 2 cells can merge */
+        for (int k = 0; k < P.L.n_players; ++k) {
+            /* any() is also the barrier that keeps lane 0's writes away from the other lanes' reads of n_cells */
+            if (c.t.any(c.pl[k].alive && c.pl[k].n_cells > 1)) {
+                if (c.lane == 0) merge_player_cells_seq(c, P, k);
+                c.t.sync();
+            }
+        }
+        if (c.h->n_viruses && c.h->n_blobs && any_virus_blob_hit(c, P)) {
+            if (c.lane == 0) virus_blob_overlap_seq(c, P);
+            c.t.sync();
+        }
+        if (any_player_mote_hit(c, P, c.vir, c.h->n_viruses, true)) {
+            if (c.lane == 0) player_virus_overlap_seq(c, P);
+            c.t.sync();
+        }
+    }
+    /* playerPelletOverlap */
+    if (!FULL) {
+        cell_eats_pellets(c, P, 0, 0, false);
+    } else {
+        bool fat_too = P.L.fat_cap > 0;
+        for (int k = 0; k < P.L.n_players; ++k) {
+            if (!c.pl[k].alive) continue;
+            for (int ci = 0; ci < c.pl[k].n_cells; ++ci) cell_eats_pellets(c, P, k, ci, fat_too && c.h->n_fat > 0);
+        }
+        if (any_player_mote_hit(c, P, c.blob, c.h->n_blobs, false)) {
+            if (c.lane == 0) player_blob_overlap_seq(c, P);
+            c.t.sync();
+        }
+        if (P.L.n_players > 1 && any_player_player_hit(c, P)) {
+            if (c.lane == 0) player_player_overlap_seq(c, P);
+            c.t.sync();
+        }
+    }
+    spawn_stuff<W, FULL>(c, P);
+}

@@ -263,7 +263,21 @@ int agar_step(AgarEnv* env, const float* actions_dev, int n_frames, void* stream
  * in one launch (one decision period = FRAME_SKIP_RATE+1 frames, aigar.py:844-849). */
 int agar_step_observe(AgarEnv* env, const float* actions_dev, int n_frames, float* obs_dev, void* stream);
 
+/* The random-action driver of BASELINE.json configs[1] ("random-action driver, 1000-step rollouts") in ONE launch:
+ * n_decisions x ( agar_observe -> action = 4 uniforms of Philox(counter = (decision_base + d, 7, env id, agent),
+ * key = seed) -> n_frames frames ).  Replaces the collector loop src/aigar.py:844-849 driven by a random
+ * learner.  obs_dev (nullable) is rewritten with every decision's observation. */
+int agar_rollout_random(AgarEnv* env, int n_decisions, int n_frames, uint32_t decision_base, float* obs_dev,
+                        void* stream);
+
 int agar_get(AgarEnv* env, AgarField which, void* out_dev, void* stream);
+
+/* lanes of a warp that cooperate on one env (1, 2, 4, 8, 16, 32; multi-cell configs: 4..32).  A tuning knob:
+ * results are identical for every width. */
+int agar_set_tile_width(AgarEnv* env, int lanes);
+int agar_get_tile_width(const AgarEnv* env);
+/* device pointer of the env records ([n_envs][record_bytes]); read-only use (checksums, DLPack export) */
+void* agar_state_ptr(const AgarEnv* env);
 
 /* parity / debugging: copy one env record device->host (synchronises `stream`) or host->device. */
 int agar_debug_dump(AgarEnv* env, int env_index, void* record_host, size_t bytes, void* stream);

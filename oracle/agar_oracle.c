@@ -145,8 +145,7 @@ static void log_ev(OracleEnv* e, int type, int a, int b, int c, int d) {
     if (e->h->n_events < e->L.event_cap) {
         AgarEvent* ev = &e->ev[e->h->n_events];
         ev->type = type, ev->a = a, ev->b = b, ev->c = c, ev->d = d;
-    } else if (e->L.event_cap > 0)
-        e->h->overflow |= AGAR_OVF_EVENT;
+    } /* a full ring just stops recording: n_events keeps counting and the running hash covers everything */
     e->h->n_events += 1;
     uint64_t hh = e->h->event_hash;
     for (int i = 0; i < 5; ++i) hh = (hh ^ (uint64_t)(uint32_t)v[i]) * 0x100000001B3ULL;
@@ -1318,6 +1317,23 @@ void oracle_get_turn(const OracleEnv* e, float* reward, uint8_t* done, uint8_t* 
     }
 }
 
+/* n_decisions x (observe -> uniform random action from Philox stream 7 -> n_frames frames): the single-env twin
+ * of agar_rollout_random (random-action driver of BASELINE config 2).  obs (nullable): float[A][L], overwritten
+ * at every decision. */
+void oracle_rollout_random(OracleEnv* e, int n_decisions, int n_frames, uint32_t decision_base, float* obs) {
+    float act[AGAR_MAX_PLAYERS * 4];
+    for (int d = 0; d < n_decisions; ++d) {
+        oracle_observe(e, obs, NULL);
+        for (int a = 0; a < e->L.n_agents; ++a) {
+            uint32_t w[4];
+            philox(decision_base + (uint32_t)d, 7u, (uint32_t)e->env_id, (uint32_t)a, (uint32_t)e->seed,
+                   (uint32_t)(e->seed >> 32), w);
+            for (int q = 0; q < 4; ++q) act[a * 4 + q] = (float)(w[q] >> 8) * (1.0f / 16777216.0f);
+        }
+        oracle_step(e, act, n_frames);
+    }
+}
+
 /* ---- batched multi-thread driver for bench.py's CPU baseline: E independent envs, T decision periods of
  * (observe; step frame_skip+1 frames) with uniform random actions (SURVEY §8d config 2 driver).  Returns
  * env-steps executed.  One pthread per requested thread, envs dealt round-robin. */
@@ -1334,17 +1350,8 @@ static void* batch_worker(void* arg) {
     for (int i = j->tid; i < j->n_envs; i += j->n_threads) {
         OracleEnv* e = oracle_create(j->cfg, j->seed, j->first_env + (uint64_t)i);
         float* obs = (float*)malloc(sizeof(float) * e->L.state_len * (e->L.n_agents ? e->L.n_agents : 1));
-        float act[AGAR_MAX_PLAYERS * 4];
-        for (int t = 0; t < j->n_decisions; ++t) {
-            oracle_observe(e, obs, NULL);
-            uint32_t w[4];
-            for (int a = 0; a < e->L.n_agents; ++a) {
-                philox((uint32_t)t, 7u, (uint32_t)e->env_id, (uint32_t)a, (uint32_t)j->seed, (uint32_t)(j->seed >> 32), w);
-                for (int q = 0; q < 4; ++q) act[a * 4 + q] = (float)(w[q] >> 8) * (1.0f / 16777216.0f);
-            }
-            oracle_step(e, act, period);
-            j->steps += (uint64_t)period;
-        }
+        oracle_rollout_random(e, j->n_decisions, period, 0, obs);
+        j->steps += (uint64_t)period * (uint64_t)j->n_decisions;
         for (int k = 0; k < e->L.n_players; ++k) j->mass_sum += total_mass(e, k);
         free(obs);
         oracle_destroy(e);

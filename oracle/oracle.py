@@ -54,6 +54,7 @@ def load(portable=False):
     lib.oracle_observe.argtypes = [vp, vp, vp]
     lib.oracle_step.argtypes = [vp, vp, i32]
     lib.oracle_get_turn.argtypes = [vp, vp, vp, vp, vp]
+    lib.oracle_rollout_random.argtypes = [vp, i32, i32, ctypes.c_uint32, vp]
     lib.oracle_rollout_batch.argtypes = [ctypes.POINTER(lay.AgarConfig), i32, u64, u64, i32, i32,
                                          ctypes.POINTER(ctypes.c_double)]
     lib.oracle_rollout_batch.restype = u64
@@ -132,6 +133,9 @@ class OracleEnv(object):
         if actions is not None:
             act[:] = np.asarray(actions, dtype=np.float32).reshape(a, 4)
         self.lib.oracle_step(self.h, act.ctypes.data, n_frames)
+
+    def rollout_random(self, n_decisions, n_frames, decision_base=0):
+        self.lib.oracle_rollout_random(self.h, n_decisions, n_frames, decision_base, self.obs.ctypes.data)
 
     def frame(self, actions=None):
         """observe + one frame, the unit RefEnv.step() performs."""
