@@ -199,6 +199,7 @@ DEV void log_ev(Ctx<W>& c, const DevParams& P, int type, int a, int b, int cc, i
         ev->type = type, ev->a = a, ev->b = b, ev->c = cc, ev->d = d;
     }
     c.h->n_events = n + 1;
+    if (type == AGAR_EV_COLLIDE) return; /* logged, not hashed (see oracle log_ev) */
     uint64_t hh = c.h->event_hash;
     hh = (hh ^ (uint64_t)(uint32_t)type) * 0x100000001B3ULL;
     hh = (hh ^ (uint64_t)(uint32_t)a) * 0x100000001B3ULL;

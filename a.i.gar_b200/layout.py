@@ -42,7 +42,7 @@ class AgarConfig(ctypes.Structure):
         ("mass_as_reward", ctypes.c_int32), ("obs_mode", ctypes.c_int32),
         ("fat_cap", ctypes.c_int32), ("virus_cap", ctypes.c_int32), ("blob_cap", ctypes.c_int32),
         ("event_cap", ctypes.c_int32),
-        ("reserved", ctypes.c_int32 * 7),
+        ("pellet_cap", ctypes.c_int32), ("reserved", ctypes.c_int32 * 6),
         ("reward_scale", ctypes.c_double), ("reward_term", ctypes.c_double),
         ("death_term", ctypes.c_double), ("death_factor", ctypes.c_double),
     ]
@@ -158,6 +158,7 @@ def layout_for_config(c):
     v0 = 0
     while v0 < L.max_viruses:
         v0 += 1
+    p = max(p, c.pellet_cap)
     L.pellet_cap = p
     L.virus_cap = (c.virus_cap if c.virus_cap > 0 else 2 * v0 + 6) if c.virus_enabled else 0
     L.blob_cap = (c.blob_cap if c.blob_cap > 0 else 8 * k + 8) if c.enable_eject else 0
@@ -253,7 +254,7 @@ def event_hash_step(h, ev):
     return h
 
 
-def compare_records(a, b, rtol=0.0, atol=0.0, what="", check_bots=True, check_events=False):
+def compare_records(a, b, rtol=0.0, atol=0.0, what="", check_bots=True, check_events=False, check_hist=True):
     """Return a list of human-readable differences between two Records (empty = equal).
 
     Integer fields must match exactly; float fields within rtol/atol (0 = bit-exact)."""
@@ -314,7 +315,7 @@ def compare_records(a, b, rtol=0.0, atol=0.0, what="", check_bots=True, check_ev
     if np.any(a.pellets != b.pellets):
         idx = int(np.argwhere(a.pellets != b.pellets)[0][0])
         diffs.append("%spellets[%d]: %#x != %#x" % (what, idx, int(a.pellets[idx]), int(b.pellets[idx])))
-    if a.hist.size:
+    if a.hist.size and check_hist:
         if rtol == 0.0 and atol == 0.0:
             bad = a.hist != b.hist
         else:

@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py — batched agar.io env-steps/s on B200 (BASELINE.json metric), one JSON line on stdout.
+
+Workload (config.workload): BASELINE.json configs[1] — pellet collection, 1 RL agent, no opponents or viruses,
+grid-vision obs; 4096 envs per GPU, random-action driver, 1000-frame rollouts.  One "step" = one 1000-frame
+rollout of every env (125 decisions x (observe -> random action -> 8 frames)), which agar_rollout_random runs
+as ONE persistent launch.  value = env-steps (frames x envs) per second with all state resident in HBM;
+e2e = the same rollout driven through agar_step_host (host action buffers in, host obs/reward/done out, copies
+inside the timed region).  Weak scaling: every rank runs its own 4096 envs, no collective on the step path
+(one NCCL all-reduce of episode statistics after the timed region).
+
+python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--envs E] [--frames F] [--tile W]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "env_steps_per_sec"
+UNIT = "env-steps/s"
+FRAME_SKIP = 7
+PERIOD = FRAME_SKIP + 1
+
+
+def algorithmic_bytes_per_env_step(p_live=85.0, c_live=1.0, vb_live=0.0, k=1, state_len=123, obs_per_frame=1.0 / PERIOD):
+    """12*P + 64*C + 48*(V+B) + 96*K + 4*L*n_obs."""
+    return 12.0 * p_live + 64.0 * c_live + 48.0 * vb_live + 96.0 * k + 4.0 * state_len * obs_per_frame
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def profiled_traffic(envs, frames):
+    """dram bytes per launch of k_main from the committed ncu summary, if it matches this launch shape."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        if int(t.get("envs", -1)) == envs and int(t.get("frames", -1)) == frames:
+            return float(t["dram_bytes_per_launch"])
+    except Exception:
+        pass
+    return None
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.out = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.out,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        res = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return res
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+            self.out.close()
+            sm, mx, reasons = [], [], set()
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            with open(self.path) as f:
+                for line in f:
+                    parts = [p.strip() for p in line.split(",")]
+                    if len(parts) < 9:
+                        continue
+                    try:
+                        sm.append(float(parts[1]))
+                        mx.append(float(parts[2]))
+                    except ValueError:
+                        continue
+                    for n, v in zip(names, parts[5:9]):
+                        if v.lower().startswith("active"):
+                            reasons.add(n)
+            os.unlink(self.path)
+            if sm:
+                sm.sort()
+                res = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        except Exception:
+            pass
+        return res
+
+
+def cpu_port_throughput(n_threads, target_s=12.0, frames=1000):
+    """The C oracle (oracle/agar_oracle.c, libm build) on the host cores: the CPU baseline / reference arm.
+    Returns (env-steps/s, description of the sample)."""
+    import aigar_b200.layout as lay
+    from oracle import oracle as orc
+    cfg = lay.derive_config()
+    decisions = frames // PERIOD
+    t0 = time.perf_counter()
+    steps, _ = orc.rollout_batch(cfg, n_threads, 11, 0, 10, n_threads)  # probe: 80 frames per thread
+    probe = max(time.perf_counter() - t0, 1e-4)
+    rate = steps / probe
+    envs = int(max(n_threads, min(4096, rate * target_s / (decisions * PERIOD))))
+    envs = max(n_threads, envs // n_threads * n_threads)
+    t0 = time.perf_counter()
+    steps, _ = orc.rollout_batch(cfg, envs, 11, 0, decisions, n_threads)
+    dt = time.perf_counter() - t0
+    return steps / dt, "%d envs x %d frames of the same workload on %d threads (%.1f s)" % (envs, decisions * PERIOD, n_threads, dt)
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  The reference is pure Python and cannot
+    travel to the GPU box, so this times its C restatement (oracle/, bit-exact against it) on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import aigar_b200.layout as lay
+    from oracle import oracle as orc
+    cfg = lay.derive_config()
+    cores = os.cpu_count() or 1
+    frames = args.frames
+    decisions = frames // PERIOD
+    # size one step to ~2 s
+    t0 = time.perf_counter()
+    steps, _ = orc.rollout_batch(cfg, cores, 11, 0, 10, cores)
+    rate = steps / max(time.perf_counter() - t0, 1e-4)
+    envs = int(max(cores, min(args.envs, rate * 2.0 / (decisions * PERIOD))))
+    envs = max(cores, envs // cores * cores)
+    for _ in range(args.warmup):
+        orc.rollout_batch(cfg, envs, 11, 0, max(decisions // 8, 1), cores)
+    t0 = time.perf_counter()
+    total = 0
+    for i in range(args.steps):
+        s, _ = orc.rollout_batch(cfg, envs, 11, 1000 * (i + 1), decisions, cores)
+        total += s
+    dt = time.perf_counter() - t0
+    v = total / dt
+    sample = "%d envs x %d frames per step (bounded sample of the %d-env workload) on %d threads" % (
+        envs, decisions * PERIOD, args.envs, cores)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.envs, frames), "envs_per_gpu": args.envs, "frames_per_step": frames},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def workload_name(envs, frames):
+    return ("configs[1]: pellet collection, 1 RL agent, no opponents/viruses, grid-vision obs; %d envs per GPU, "
+            "random-action driver, %d-frame rollouts (frame-skip 7, obs every 8th frame)" % (envs, frames))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--envs", type=int, default=4096)
+    ap.add_argument("--frames", type=int, default=1000)
+    ap.add_argument("--tile", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import aigar_b200.layout as lay
+    from aigar_b200.env import AgarBatch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    E, frames = args.envs, args.frames
+    decisions = frames // PERIOD
+    frames = decisions * PERIOD
+    cfg = lay.derive_config()
+    batch = AgarBatch(cfg, E, device=local, seed=2026, first_env_id=rank * E, tile_width=args.tile or None)
+    L = batch.layout
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=batch.device)
+
+    def one_step(i):
+        batch.rollout_random(decisions, PERIOD, decision_base=i * decisions)
+
+    for i in range(args.warmup):
+        one_step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = batch.launch_count
+    evs = []
+    barrier()
+    for i in range(args.steps):
+        flush.fill_(i & 0xff)  # evict L2 between timed steps (126 MB L2 < 256 MiB)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        one_step(args.warmup + i)
+        e.record()
+        evs.append((s, e))
+    barrier()
+    launches = batch.launch_count - launches0
+    clocks = sampler.stop()
+    kernel_ms = [s.elapsed_time(e) for s, e in evs]
+    total_ms = float(sum(kernel_ms))
+    t = torch.tensor([total_ms], dtype=torch.float64, device=batch.device)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = world * E * frames * args.steps / (total_ms * 1e-3)
+
+    # ---- e2e: host buffers through agar_step_host (actions H2D, obs/reward/done D2H every decision)
+    e2e = None
+    if not args.no_e2e:
+        A = max(L.n_agents, 1)
+        acts = torch.rand((decisions, E, A, 4), dtype=torch.float32).pin_memory().numpy()
+        obs_h = torch.empty((E, A, L.state_len), dtype=torch.float32).pin_memory().numpy()
+        rew_h = torch.empty((E, A), dtype=torch.float32).pin_memory().numpy()
+        done_h = torch.empty((E, A), dtype=torch.uint8).pin_memory().numpy()
+        e2e_steps = min(args.steps, 5)
+        for d in range(min(decisions, 16)):
+            batch.step_host(acts[d], PERIOD, obs_h, rew_h, done_h)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            for d in range(decisions):
+                batch.step_host(acts[d], PERIOD, obs_h, rew_h, done_h)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=batch.device)
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        e2e = {"value": world * E * frames * e2e_steps / dt, "unit": UNIT,
+               "h2d_bytes_per_step": int(decisions * acts[0].nbytes),
+               "d2h_bytes_per_step": int(decisions * (obs_h.nbytes + rew_h.nbytes + done_h.nbytes)),
+               "steps": e2e_steps, "calls_per_step": decisions, "api": "agar_step_host (C ABI, pinned host buffers)"}
+
+    # ---- episode statistics: the one optional collective, outside the timed region
+    stats = batch.get(lay.GET_STATS).sum(dim=(0, 1))
+    ovf = (batch.get(lay.GET_OVERFLOW) != 0).sum().to(torch.float64)
+    if dist is not None:
+        dist.all_reduce(stats)
+        dist.all_reduce(ovf)
+    mean_mass = float(stats[0].item() / max(stats[2].item(), 1.0))
+
+    # ---- extra: the HBM-resident regime (state >> L2), same kernel
+    extra = {}
+    if not args.no_extra and rank == 0:
+        try:
+            E2, d2 = 262144, 25
+            b2 = AgarBatch(cfg, E2, device=local, seed=2026, first_env_id=10 ** 6)
+            for i in range(3):
+                b2.rollout_random(d2, PERIOD, decision_base=i * d2)
+            ts = []
+            for i in range(5):
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                b2.rollout_random(d2, PERIOD, decision_base=(3 + i) * d2)
+                e.record()
+                torch.cuda.synchronize()
+                ts.append(s.elapsed_time(e))
+            ms = sum(ts) / len(ts)
+            v2 = E2 * d2 * PERIOD / (ms * 1e-3)
+            peak, _ = measured_peak()
+            extra["envs_262144"] = {"value": v2, "unit": UNIT, "ms_per_launch": ms, "frames_per_launch": d2 * PERIOD,
+                                    "state_bytes": int(E2 * L.record_bytes), "tile_width": b2.tile_width,
+                                    "roofline_frac": v2 * algorithmic_bytes_per_env_step() / 1e9 / peak}
+            b2.close()
+        except Exception as ex:  # never lose the headline line to the side measurement
+            extra["envs_262144"] = {"error": str(ex)[:200]}
+
+    if dist is not None:
+        dist.barrier()
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = measured_peak()
+    bytes_per = algorithmic_bytes_per_env_step()
+    launch_ms = total_ms / args.steps
+    achieved = E * frames * bytes_per / (launch_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": profiled_traffic(E, frames), "kernel": "k_main<W,false>", "peak_source": peak_src,
+                "bytes_per_env_step": bytes_per, "env_steps_per_launch": E * frames, "launch_ms": launch_ms}
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        v, sample = cpu_port_throughput(cores)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": launch_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": workload_name(E, frames), "envs_per_gpu": E, "frames_per_step": frames,
+                       "l2": "flushed between timed steps (256 MiB write)", "tile_width": batch.tile_width,
+                       "record_bytes": int(L.record_bytes), "parallelism": "env-sharded x%d, no collective on the step path" % world},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "episode_stats": {"mean_mass": mean_mass, "envs_with_pool_overflow": int(ovf.item())}, "extra": extra}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -71,7 +71,8 @@ typedef struct AgarConfig {
     int32_t virus_cap;                    /* virus pool          (0 = default)                       */
     int32_t blob_cap;                     /* ejected-blob pool   (0 = default)                       */
     int32_t event_cap;                    /* per-frame event log entries per env (0 = no log)        */
-    int32_t reserved[7];
+    int32_t pellet_cap;                   /* integer-pellet slots; 0 = default (the refill target, field.py:65) */
+    int32_t reserved[6];
     double reward_scale;                  /* REWARD_SCALE :70 */
     double reward_term;                   /* REWARD_TERM  :69 */
     double death_term;                    /* DEATH_TERM   :71 */
@@ -159,7 +160,7 @@ typedef struct AgarEnvHeader {
     int32_t n_events;          /* events logged for the last stepped frame          */
     uint32_t overflow;         /* AGAR_OVF_* bits, sticky                           */
     uint32_t pad0;
-    uint64_t event_hash;       /* order-sensitive running hash of ALL events since reset */
+    uint64_t event_hash;       /* order-sensitive running hash of all events since reset except COLLIDE */
     int32_t dead_order[AGAR_MAX_PLAYERS];   /* field.deadPlayers as player indices  */
 } AgarEnvHeader;
 enum { AGAR_OVF_FAT = 1u, AGAR_OVF_VIRUS = 2u, AGAR_OVF_BLOB = 4u, AGAR_OVF_EVENT = 8u };

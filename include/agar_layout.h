@@ -43,6 +43,7 @@ static inline int agar_layout_compute(const AgarConfig* c, AgarLayout* L) {
     L->max_viruses = (double)(S * S) * 0.00005;
     int P = 0;
     while ((double)P < L->max_pellets) ++P; /* while len(pellets) < maxCollectibleCount: spawn */
+    if (c->pellet_cap > P) P = c->pellet_cap; /* extra slots never get refilled: spawning stops at max_pellets */
     L->pellet_cap = P;
     int V0 = 0;
     while ((double)V0 < L->max_viruses) ++V0;

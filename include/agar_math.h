@@ -123,11 +123,12 @@ AGAR_HD double agar_round_dec(double x, double scale) {
     double p = x * scale;
     double e = fma(x, scale, -p); /* x*scale == p + e exactly */
     double n = rint(p);           /* ties-to-even on p */
-    double f = (p - n) + e;       /* exact: |p - n| <= 0.5 and both small */
-    if (f > 0.5 || (f == 0.5 && fmod(n, 2.0) != 0.0))
-        n += 1.0;
-    else if (f < -0.5 || (f == -0.5 && fmod(n, 2.0) != 0.0))
-        n -= 1.0;
+    double d = p - n;             /* exact, |d| <= 0.5; p, n and 0.5 are multiples of ulp(p), |e| <= ulp(p)/2, */
+    if (d == 0.5) {               /* so only an exact tie of p can be moved across the half by e               */
+        if (e > 0.0) n += 1.0;    /* true value above the tie (rint went down to the even neighbour)           */
+    } else if (d == -0.5) {
+        if (e < 0.0) n -= 1.0;
+    }
     return n / scale;
 }
 

@@ -147,6 +147,9 @@ static void log_ev(OracleEnv* e, int type, int a, int b, int c, int d) {
         ev->type = type, ev->a = a, ev->b = b, ev->c = c, ev->d = d;
     } /* a full ring just stops recording: n_events keeps counting and the running hash covers everything */
     e->h->n_events += 1;
+    /* COLLIDE is logged but not hashed: the re-test of a pair that was just pushed apart to distance == r1 + r2
+     * is decided by the last bit of the positions, and it changes no discrete state */
+    if (type == AGAR_EV_COLLIDE) return;
     uint64_t hh = e->h->event_hash;
     for (int i = 0; i < 5; ++i) hh = (hh ^ (uint64_t)(uint32_t)v[i]) * 0x100000001B3ULL;
     e->h->event_hash = hh;
@@ -1377,4 +1380,19 @@ uint64_t oracle_rollout_batch(const AgarConfig* cfg, int n_envs, uint64_t seed, 
     }
     if (mass_sum_out) *mass_sum_out = mass;
     return steps;
+}
+
+/* ---- thin exports of include/agar_math.h so that tests can bound the portable math against libm / Python */
+double oracle_pm_pow(double x, double y) { return agar_pow(x, y); }
+double oracle_pm_log(double x) { return agar_log(x); }
+double oracle_pm_exp(double x) { return agar_exp(x); }
+void oracle_pm_dir(double dy, double dx, double* c, double* s) { agar_dir(dy, dx, c, s); }
+double oracle_pm_round_dec(double x, double scale) { return agar_round_dec(x, scale); }
+/* spatialHashTable.py:70-83 for one axis, exported for the closed-form pellet-rectangle proof in tests */
+void oracle_axis_range(double p, double radius, int S, int* b0, int* b1) { axis_range(p, radius, S, b0, b1); }
+/* Field.update() alone (field.py:85-92), for the hand-placed known-answer scenes of SURVEY.md App. B */
+void oracle_field_update(OracleEnv* e) {
+    e->h->n_events = 0;
+    field_update(e);
+    e->h->frame += 1;
 }

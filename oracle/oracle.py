@@ -54,6 +54,17 @@ def load(portable=False):
     lib.oracle_observe.argtypes = [vp, vp, vp]
     lib.oracle_step.argtypes = [vp, vp, i32]
     lib.oracle_get_turn.argtypes = [vp, vp, vp, vp, vp]
+    lib.oracle_field_update.argtypes = [vp]
+    lib.oracle_pm_pow.argtypes = [ctypes.c_double, ctypes.c_double]
+    lib.oracle_pm_pow.restype = ctypes.c_double
+    lib.oracle_pm_log.argtypes = [ctypes.c_double]
+    lib.oracle_pm_log.restype = ctypes.c_double
+    lib.oracle_pm_exp.argtypes = [ctypes.c_double]
+    lib.oracle_pm_exp.restype = ctypes.c_double
+    lib.oracle_pm_dir.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+    lib.oracle_pm_round_dec.argtypes = [ctypes.c_double, ctypes.c_double]
+    lib.oracle_pm_round_dec.restype = ctypes.c_double
+    lib.oracle_axis_range.argtypes = [ctypes.c_double, ctypes.c_double, i32, ctypes.POINTER(i32), ctypes.POINTER(i32)]
     lib.oracle_rollout_random.argtypes = [vp, i32, i32, ctypes.c_uint32, vp]
     lib.oracle_rollout_batch.argtypes = [ctypes.POINTER(lay.AgarConfig), i32, u64, u64, i32, i32,
                                          ctypes.POINTER(ctypes.c_double)]
@@ -133,6 +144,9 @@ class OracleEnv(object):
         if actions is not None:
             act[:] = np.asarray(actions, dtype=np.float32).reshape(a, 4)
         self.lib.oracle_step(self.h, act.ctypes.data, n_frames)
+
+    def field_update(self):
+        self.lib.oracle_field_update(self.h)
 
     def rollout_random(self, n_decisions, n_frames, decision_base=0):
         self.lib.oracle_rollout_random(self.h, n_decisions, n_frames, decision_base, self.obs.ctypes.data)

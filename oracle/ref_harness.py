@@ -138,6 +138,21 @@ def load_reference():
 
     ns.sht.spatialHashTable.getObjectsFromBuckets = getObjectsFromBuckets
 
+    # (iii') optional obs-grid canonicalisation (AGAR_OBS_CANONICAL): spatialHashTable.py:19 computes
+    # cols = int(ceil(size / bucket)); for the FOV grids size / (size / G) sometimes rounds to G + 2^-49 and the
+    # table gets G + 1 columns.  Canonical mode rounds the quotient to 9 decimals first.
+    orig_sht_init = ns.sht.spatialHashTable.__init__
+
+    def sht_init(self, hashTableSize, bucketSize, left=0, top=0):
+        orig_sht_init(self, hashTableSize, bucketSize, left, top)
+        if _current is not None and _current.cfg.obs_mode == lay.OBS_CANONICAL:
+            self.rows = int(math.ceil(round(hashTableSize / bucketSize, 9)))
+            self.cols = self.rows
+            self.buckets = {}
+            self.clearBuckets()
+
+    ns.sht.spatialHashTable.__init__ = sht_init
+
     # (iii) bookkeeping
     Cell, Field = ns.cell.Cell, ns.field.Field
     orig_cell_init = Cell.__init__
@@ -428,7 +443,8 @@ class RefEnv(object):
     def log(self, typ, a=0, b=0, c=0, d=0):
         ev = (int(typ), int(a), int(b), int(c), int(d))
         self.events.append(ev)
-        self.event_hash = lay.event_hash_step(self.event_hash, ev)
+        if ev[0] != lay.EV_COLLIDE:  # logged, not hashed: a touching pair's re-test hangs on the last bit
+            self.event_hash = lay.event_hash_step(self.event_hash, ev)
 
     def alloc(self, slots):
         for i, s in enumerate(slots):

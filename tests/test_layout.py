@@ -1,0 +1,67 @@
+"""Host logic: record layout (C header == Python twin), struct sizes, the closed-form pellet hash rectangle."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import aigar_b200.layout as lay
+from oracle import oracle as orc
+
+CONFIGS = [dict(), dict(num_nn=1, num_greedy=1, virus=True, split=True, eject=True),
+           dict(num_nn=8, num_greedy=8, virus=True, split=True, eject=True),
+           dict(num_nn=8, num_greedy=8, virus=False, split=True, eject=True),
+           dict(num_nn=2, num_random=1, split=True)]
+
+
+@pytest.mark.parametrize("kw", CONFIGS)
+def test_c_layout_equals_python_layout(kw):
+    cfg = lay.derive_config(event_cap=32, **kw)
+    c = lay.AgarLayout()
+    assert orc.load().oracle_layout(ctypes.byref(cfg), ctypes.byref(c)) == 0
+    assert c.as_dict() == lay.layout_for_config(cfg).as_dict()
+    assert c.record_bytes % 128 == 0
+
+
+def test_sizes_match_the_survey():
+    for k, (s, p, l) in {1: (75, 85, 123), 2: (106, 169, 854), 16: (300, 1350, 854)}.items():
+        cfg = lay.derive_config(num_nn=1, num_greedy=k - 1, virus=k > 1, split=k > 1, eject=k > 1)
+        L = lay.layout_for_config(cfg)
+        assert (L.field_size, L.pellet_cap, L.state_len) == (s, p, l)
+    cfg = lay.derive_config(num_nn=8, num_greedy=8, virus=False, split=True, eject=True)
+    assert lay.layout_for_config(cfg).state_len == 733
+
+
+def test_invalid_configs_are_rejected():
+    lib = orc.load()
+    out = lay.AgarLayout()
+    bad = lay.derive_config()
+    bad.n_players = 0
+    assert lib.oracle_layout(ctypes.byref(bad), ctypes.byref(out)) == -1
+    bad = lay.derive_config(eject=True)  # eject without split raises in the reference (bot.py:568)
+    assert lib.oracle_layout(ctypes.byref(bad), ctypes.byref(out)) == -4
+    bad = lay.derive_config(num_nn=1, num_greedy=1)
+    bad.bot_type[0], bad.bot_type[1] = lay.BOT_GREEDY, lay.BOT_NN  # NN bots must come first (aigar.py:778-780)
+    assert lib.oracle_layout(ctypes.byref(bad), ctypes.byref(out)) == -1
+
+
+def test_pellet_rectangle_closed_form():
+    """The kernels use an integer formula for the hash rectangle of an integer pellet; prove it equal to
+    spatialHashTable.getIdsForArea (float arithmetic) for every coordinate, mass and field size."""
+    lib = orc.load()
+    b0, b1 = ctypes.c_int(), ctypes.c_int()
+    for S in (75, 106, 300, 1023):
+        for m in (1, 2, 3):
+            r = float(np.sqrt(m / np.pi))
+            for x in range(S):
+                lib.oracle_axis_range(float(x), r, S, ctypes.byref(b0), ctypes.byref(b1))
+                assert (b0.value, b1.value) == ((x - 1 if x > 0 else 0) // 20, x // 20), (S, m, x)
+
+
+def test_sharding_partition():
+    from aigar_b200.sharding import shard_envs
+    for total in (1, 7, 4096, 65536 + 3):
+        for world in (1, 2, 3, 8):
+            spans = [shard_envs(total, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and sum(n for _, n in spans) == total
+            for (f0, n0), (f1, _) in zip(spans, spans[1:]):
+                assert f0 + n0 == f1

@@ -1,0 +1,43 @@
+"""Live pin of the oracle: the unmodified reference Python (imported from /root/reference/src through
+oracle/ref_harness.py) and oracle/agar_oracle.c stepped side by side, records / events / observations compared
+BIT FOR BIT every frame.  Skipped where the reference checkout is absent (the GPU box): tests/golden/ carries
+the same evidence there."""
+import pytest
+
+from oracle import ref_harness as rh
+
+pytestmark = pytest.mark.skipif(not rh.reference_available(), reason="reference checkout not present")
+
+
+@pytest.mark.parametrize("which,frames,seed", [("1", 400, 11), ("1", 250, 12), ("3", 500, 13), ("r", 300, 14), ("4", 40, 15),
+                                               ("4nv", 30, 16)])
+def test_oracle_equals_reference(which, frames, seed):
+    import compare_oracle_ref as cmp
+    kws = {"1": dict(), "3": dict(num_nn=1, num_greedy=1, virus=True, split=True, eject=True),
+           "4": dict(num_nn=8, num_greedy=8, virus=True, split=True, eject=True),
+           "r": dict(num_nn=1, num_greedy=1, num_random=1, virus=True, split=True, eject=True),
+           "4nv": dict(num_nn=8, num_greedy=8, virus=False, split=True, eject=True)}
+    assert cmp.run(kws[which], frames, seed=seed, verbose=False)
+
+
+def test_reset_matches_reference():
+    import numpy as np
+    import aigar_b200.layout as lay
+    from oracle import oracle as orc
+    cfg = lay.derive_config(num_nn=1, num_greedy=1, virus=True, split=True, eject=True, event_cap=256)
+    ref, ora = rh.RefEnv(cfg, seed=5, env_id=1), orc.OracleEnv(cfg, seed=5, env_id=1)
+    rng = np.random.default_rng(0)
+    for t in range(120):
+        a = rng.random((1, 4)).astype(np.float32)
+        ref.step(a)
+        ora.frame(a)
+    ref.reset(), ref.reset_bots()
+    ora.reset(), ora.reset_bots()
+    d = lay.compare_records(ref.to_record(), ora.record, what="after reset ", check_events=False)
+    assert not d, d
+    for t in range(60):
+        a = rng.random((1, 4)).astype(np.float32)
+        tr = ref.step(a)
+        ora.frame(a)
+    d = lay.compare_records(ref.to_record(tr), ora.record, what="after reset+60 ")
+    assert not d, d

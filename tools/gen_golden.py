@@ -1,0 +1,57 @@
+"""Generate tests/golden/*.npz by EXECUTING the reference (NILOIDE/A.I.gar, /root/reference/src) through
+oracle/ref_harness.py.  Run in the build container only (the reference is absent on the GPU box).
+
+Each fixture holds, for one (config, seed, env id): the float32 actions fed per frame, the env record after
+selected frames, the running event hash after every frame, and every observation the NN agents received
+(float32, as the API returns them).  tests/test_golden.py replays the actions through the C oracle (bit-exact)
+and tests/test_gpu_parity.py through the CUDA path."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import aigar_b200.layout as lay
+from oracle import ref_harness as rh
+
+CASES = {
+    "cfg1_pellet": (dict(), 640, 3, 17, 80),
+    "cfg3_1v1": (dict(num_nn=1, num_greedy=1, virus=True, split=True, eject=True), 480, 5, 2, 60),
+    "cfg3_random_bot": (dict(num_nn=1, num_greedy=1, num_random=1, virus=True, split=True, eject=True), 320, 7, 1, 80),
+    "cfg4_arena": (dict(num_nn=8, num_greedy=8, virus=True, split=True, eject=True), 96, 9, 4, 24),
+    # obs_mode = AGAR_OBS_CANONICAL: the FOV grid always has G columns (the harness patches spatialHashTable.__init__)
+    "cfg1_pellet_canonical": (dict(obs_mode=1), 640, 3, 17, 80),
+    "cfg3_1v1_canonical": (dict(num_nn=1, num_greedy=1, virus=True, split=True, eject=True, obs_mode=1), 480, 5, 2, 60),
+}
+
+
+def generate(name, kw, frames, seed, env_id, every):
+    cfg = lay.derive_config(event_cap=0, **kw)
+    ref = rh.RefEnv(cfg, seed=seed, env_id=env_id)
+    L = ref.layout
+    A = max(L.n_agents, 1)
+    rng = np.random.default_rng(seed * 7919 + env_id)
+    actions = rng.random((frames, A, 4)).astype(np.float32)
+    recs, rec_frames, hashes = [ref.to_record().buf.copy()], [-1], []
+    obs_list, obs_idx, flags = [], [], []
+    for t in range(frames):
+        tr = ref.step(actions[t])
+        for a in range(L.n_agents):
+            flags.append((t, a, int(tr[a]["observed"]), int(tr[a]["valid"]), int(tr[a]["done"]), int(tr[a]["need_action"])))
+            if tr[a]["obs"] is not None:
+                obs_list.append(tr[a]["obs"].astype(np.float32))
+                obs_idx.append((t, a))
+        hashes.append(ref.event_hash)
+        if (t + 1) % every == 0 or t == frames - 1:
+            recs.append(ref.to_record(tr).buf.copy())
+            rec_frames.append(t)
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", name + ".npz")
+    np.savez_compressed(out, kw=np.array(repr(kw)), seed=seed, env_id=env_id, actions=actions,
+                        records=np.stack(recs), record_frames=np.array(rec_frames), event_hash=np.array(hashes, dtype=np.uint64),
+                        obs=np.stack(obs_list) if obs_list else np.zeros((0, L.state_len), np.float32),
+                        obs_index=np.array(obs_idx, dtype=np.int32).reshape(-1, 2), flags=np.array(flags, dtype=np.int32))
+    print(name, os.path.getsize(out), "bytes;", len(recs), "records;", len(obs_list), "observations")
+
+
+if __name__ == "__main__":
+    for name, (kw, frames, seed, env_id, every) in CASES.items():
+        if len(sys.argv) > 1 and name not in sys.argv[1:]:
+            continue
+        generate(name, kw, frames, seed, env_id, every)
