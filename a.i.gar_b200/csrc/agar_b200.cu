@@ -13,6 +13,7 @@
 #include "../../include/agar_layout.h"
 #include "agar_bots.cuh"
 #include "agar_dev.cuh"
+#include "agar_simple.cuh"
 
 extern __shared__ __align__(16) uint8_t g_smem[];
 
@@ -108,6 +109,82 @@ k_main(const __grid_constant__ DevParams P, uint8_t* __restrict__ state, const f
             for (int a = 0; a < A; ++a) nn_turn_begin<W, FULL>(c, P, a, obs_env ? obs_env + (size_t)a * SL : nullptr);
     }
     stage_out(P, state, env0, n_here);
+}
+
+
+/* ------------------------------------------------------------------ register-resident kernel (agar_simple.cuh) */
+struct SimplePlan {
+    int strideB; /* bytes between the staged [pellets .. end of record] regions of consecutive envs */
+};
+template <int W>
+__global__ void __launch_bounds__(128)
+k_simple(const __grid_constant__ DevParams P, const SimplePlan SP, uint8_t* __restrict__ state, const float* __restrict__ actions,
+         float* __restrict__ obs, int n_frames, int n_dec, int flags, uint32_t dec_base) {
+    const int per = blockDim.x / W; /* envs per CTA */
+    const int env0 = blockIdx.x * per;
+    const int n_here = min(per, P.n_envs - env0);
+    const int rec_words = (int)(P.L.record_bytes / 4), pel_word = (int)(P.L.off_pellets / 4);
+    const int tail_words = rec_words - pel_word;
+    {   /* stage the pellet pool (+ event ring) in: coalesced 4-byte words; spare slots replicate the last env so that
+         * every lane of a partly filled warp runs well-defined work */
+        for (int i = threadIdx.x; i < per * tail_words; i += blockDim.x) {
+            int e = i / tail_words, w = i - e * tail_words;
+            int es = e < n_here ? e : n_here - 1;
+            const uint32_t* src = (const uint32_t*)(state + (size_t)(env0 + es) * P.L.record_bytes) + pel_word;
+            *(uint32_t*)(g_smem + (size_t)e * SP.strideB + w * 4) = src[w];
+        }
+    }
+    __syncthreads();
+    const int slot = threadIdx.x / W, sub = threadIdx.x % W;
+    const bool valid = slot < n_here;
+    const int env = env0 + (valid ? slot : n_here - 1);
+    const uint32_t env_id = (uint32_t)(P.first_env + (uint64_t)env);
+    uint8_t* rec = state + (size_t)env * P.L.record_bytes;
+    uint8_t* b = g_smem + (size_t)slot * SP.strideB;
+    SPtr q;
+    q.h = (AgarEnvHeader*)(rec + P.L.off_header);
+    q.p = (AgarPlayer*)(rec + P.L.off_players);
+    q.c = (AgarCell*)(rec + P.L.off_cells);
+    q.pel = (uint32_t*)b;
+    q.ev = (AgarEvent*)(b + (P.L.off_events - P.L.off_pellets));
+    SReg r;
+    s_load(r, q);
+    float* row = (obs != nullptr && valid) ? obs + (size_t)env * P.L.state_len : nullptr;
+    for (int d = 0; d < n_dec; ++d) {
+        if (flags & KF_OBS_BEFORE) {
+            int d_o = s_turn_begin(r, P);
+            s_observe<W>(r, q, P, d_o != 0, row, sub);
+        }
+        for (int f = 0; f < n_frames; ++f) {
+            r.n_events = 0;
+            int d_o = s_turn_begin(r, P);
+            s_observe<W>(r, q, P, d_o != 0, nullptr, sub);
+            float act[4] = {0.f, 0.f, 0.f, 0.f};
+            if (r.need_action) {
+                if (flags & KF_RANDOM_ACTIONS) {
+                    uint32_t w[4];
+                    philox(dec_base + (uint32_t)d, 7u, env_id, 0u, (uint32_t)P.seed, (uint32_t)(P.seed >> 32), w);
+                    for (int i = 0; i < 4; ++i) act[i] = (float)(w[i] >> 8) * (1.0f / 16777216.0f);
+                } else {
+                    const float* ap = actions + (size_t)env * 4;
+                    for (int i = 0; i < 4; ++i) act[i] = ap[i];
+                }
+            }
+            s_turn_end(r, P, act);
+            s_field_update<W>(r, q, P, env_id, sub);
+        }
+    }
+    if (flags & KF_OBS_AFTER) {
+        int d_o = s_turn_begin(r, P);
+        s_observe<W>(r, q, P, d_o != 0, row, sub);
+    }
+    if (valid && sub == 0) s_store(r, q);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_here * tail_words; i += blockDim.x) { /* stage the pools out */
+        int e = i / tail_words, w = i - e * tail_words;
+        uint32_t* dst = (uint32_t*)(state + (size_t)(env0 + e) * P.L.record_bytes) + pel_word;
+        dst[w] = *(const uint32_t*)(g_smem + (size_t)e * SP.strideB + w * 4);
+    }
 }
 
 /* mode 0: Model(...) + createBot*K + Model.initialize (model.py:51,154-162,90-94; field.py:57-67)
@@ -217,6 +294,11 @@ struct AgarEnv {
     double* deg_tab;
     int n_envs, device, W, full, threads, tiles;
     size_t smem_bytes;
+    int init_W, init_threads, init_tiles;
+    size_t init_smem;
+    SimplePlan sp;
+    int simple_W, simple_threads;
+    size_t simple_smem;
     int64_t launches;
     char err[256];
     /* step_host staging */
@@ -273,10 +355,10 @@ static cudaError_t launch_main_t(AgarEnv* e, const float* actions, float* obs, i
 }
 template <int W, bool FULL>
 static cudaError_t launch_init_t(AgarEnv* e, const uint8_t* mask, int mode, cudaStream_t s) {
-    cudaError_t err = cudaFuncSetAttribute(k_init<W, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes);
+    cudaError_t err = cudaFuncSetAttribute(k_init<W, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->init_smem);
     if (err != cudaSuccess) return err;
-    int blocks = (e->n_envs + e->tiles - 1) / e->tiles;
-    k_init<W, FULL><<<blocks, e->threads, e->smem_bytes, s>>>(e->P, e->state, mask, mode);
+    int blocks = (e->n_envs + e->init_tiles - 1) / e->init_tiles;
+    k_init<W, FULL><<<blocks, e->init_threads, e->init_smem, s>>>(e->P, e->state, mask, mode);
     return cudaGetLastError();
 }
 #define DISPATCH(fn, ...)                                                 \
@@ -286,16 +368,31 @@ static cudaError_t launch_init_t(AgarEnv* e, const uint8_t* mask, int mode, cuda
                              : fn<4, true>(__VA_ARGS__))                  \
              : (e->W == 32  ? fn<32, false>(__VA_ARGS__)                  \
                 : e->W == 16 ? fn<16, false>(__VA_ARGS__)                 \
-                : e->W == 8  ? fn<8, false>(__VA_ARGS__)                  \
-                : e->W == 4  ? fn<4, false>(__VA_ARGS__)                  \
-                : e->W == 2  ? fn<2, false>(__VA_ARGS__)                  \
-                             : fn<1, false>(__VA_ARGS__)))
+                             : fn<16, false>(__VA_ARGS__)))
 
 static int launch_main(AgarEnv* e, const float* actions, float* obs, int n_frames, int n_dec, int flags, uint32_t dec_base,
                        void* stream) {
     AgarEnv* env = e;
     CU(cudaSetDevice(e->device));
-    cudaError_t err = DISPATCH(launch_main_t, e, actions, obs, n_frames, n_dec, flags, dec_base, (cudaStream_t)stream);
+    cudaError_t err;
+    if (e->simple_W) {
+        int blocks = (e->n_envs * e->simple_W + e->simple_threads - 1) / e->simple_threads;
+#define LAUNCH_SIMPLE(WW)                                                                                                     \
+    do {                                                                                                                      \
+        err = cudaFuncSetAttribute(k_simple<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->simple_smem);           \
+        if (err == cudaSuccess) {                                                                                             \
+            k_simple<WW><<<blocks, e->simple_threads, e->simple_smem, (cudaStream_t)stream>>>(e->P, e->sp, e->state, actions, obs, \
+                                                                                              n_frames, n_dec, flags, dec_base);  \
+            err = cudaGetLastError();                                                                                         \
+        }                                                                                                                     \
+    } while (0)
+        if (e->simple_W == 1) LAUNCH_SIMPLE(1);
+        else if (e->simple_W == 2) LAUNCH_SIMPLE(2);
+        else if (e->simple_W == 4) LAUNCH_SIMPLE(4);
+        else LAUNCH_SIMPLE(8);
+#undef LAUNCH_SIMPLE
+    } else
+        err = DISPATCH(launch_main_t, e, actions, obs, n_frames, n_dec, flags, dec_base, (cudaStream_t)stream);
     if (err != cudaSuccess) return fail(e, AGAR_E_CUDA, "kernel launch failed: %s", cudaGetErrorString(err));
     e->launches += 1;
     return AGAR_OK;
@@ -303,17 +400,38 @@ static int launch_main(AgarEnv* e, const float* actions, float* obs, int n_frame
 static int launch_init(AgarEnv* e, const uint8_t* mask, int mode, void* stream) {
     AgarEnv* env = e;
     CU(cudaSetDevice(e->device));
-    cudaError_t err = DISPATCH(launch_init_t, e, mask, mode, (cudaStream_t)stream);
+    cudaError_t err = e->full ? (e->init_W == 32 ? launch_init_t<32, true>(e, mask, mode, (cudaStream_t)stream)
+                                                  : launch_init_t<8, true>(e, mask, mode, (cudaStream_t)stream))
+                              : launch_init_t<32, false>(e, mask, mode, (cudaStream_t)stream);
     if (err != cudaSuccess) return fail(e, AGAR_E_CUDA, "kernel launch failed: %s", cudaGetErrorString(err));
     e->launches += 1;
     return AGAR_OK;
 }
 
+/* Lanes per env.  Single-cell pellet-collection configs: 1, 2, 4, 8 select the register-resident kernel
+ * (agar_simple.cuh), 16 / 32 the general kernel; every other config: 4, 8, 16, 32 (general kernel). */
 extern "C" int agar_set_tile_width(AgarEnv* e, int W) {
     if (!e) return AGAR_E_INVALID;
-    bool ok = e->full ? (W == 4 || W == 8 || W == 16 || W == 32) : (W == 1 || W == 2 || W == 4 || W == 8 || W == 16 || W == 32);
+    if (!e->full && (W == 1 || W == 2 || W == 4 || W == 8)) {
+        int tail_words = (int)((e->L.record_bytes - e->L.off_pellets) / 4);
+        e->sp.strideB = (tail_words | 1) * 4;
+        if (e->L.pellet_cap > 128 * W) return fail(e, AGAR_E_UNSUPPORTED, "pellet pool too large for this tile width%s", "");
+        int threads = 64;
+        const char* tenv = getenv("AGAR_SIMPLE_THREADS");
+        if (tenv && atoi(tenv) >= 32) threads = atoi(tenv) / 32 * 32;
+        if (threads > 128) threads = 128;
+        size_t per_env = (size_t)e->sp.strideB;
+        while (threads > 32 && per_env * (threads / W) > 200 * 1024) threads -= 32;
+        e->simple_W = W;
+        e->simple_threads = threads;
+        e->simple_smem = per_env * (threads / W);
+        e->W = W;
+        return AGAR_OK;
+    }
+    bool ok = (W == 16 || W == 32) || (e->full && (W == 4 || W == 8));
     if (!ok) return fail(e, AGAR_E_INVALID, "unsupported tile width%s", "");
     if (!plan_launch(e, W)) return fail(e, AGAR_E_NOMEM, "env record does not fit in shared memory%s", "");
+    e->simple_W = 0;
     return AGAR_OK;
 }
 extern "C" int agar_get_tile_width(const AgarEnv* e) { return e ? e->W : 0; }
@@ -374,7 +492,14 @@ extern "C" int agar_create(const AgarConfig* cfg, int n_envs, int device, uint64
     CU(cudaMemcpyAsync(e->deg_tab, tab, sizeof tab, cudaMemcpyHostToDevice, (cudaStream_t)stream));
     CU(cudaStreamSynchronize((cudaStream_t)stream)); /* tab is a stack buffer */
     P.deg_tab = e->deg_tab;
-    int W = e->full ? 32 : (n_envs >= 65536 ? 4 : (n_envs >= 16384 ? 8 : 32));
+    {   /* k_init always runs with 32-lane tiles (8 if a record is too big for four tiles... it is not hot) */
+        if (!plan_launch(e, 32)) {
+            cudaFree(e->state), cudaFree(e->deg_tab), free(e);
+            return fail(nullptr, AGAR_E_NOMEM, "env record does not fit in shared memory%s", "");
+        }
+        e->init_W = 32, e->init_threads = e->threads, e->init_tiles = e->tiles, e->init_smem = e->smem_bytes;
+    }
+    int W = e->full ? 32 : (n_envs <= 16384 ? 8 : (n_envs <= 131072 ? 2 : 1));
     const char* wenv = getenv("AGAR_TILE_W");
     if (wenv && atoi(wenv) > 0) W = atoi(wenv);
     if (agar_set_tile_width(e, W) != AGAR_OK && agar_set_tile_width(e, 32) != AGAR_OK) {
