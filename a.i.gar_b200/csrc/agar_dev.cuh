@@ -82,7 +82,8 @@ struct Rect {
 /* spatialHashTable.py:70-83 getIdsForArea, one axis */
 DEV void axis_range(double p, double radius, int S, int& b0, int& b1) {
     double cl = py_max0(p - radius);
-    int bucket_left = (int)(cl - fmod(cl, (double)AG_BUCKET));
+    /* int(cl - cl % 20) == 20 * floor(cl / 20) exactly (fmod is exact); in integers: floor(floor(cl) / 20) */
+    int bucket_left = ((int)cl / AG_BUCKET) * AG_BUCKET;
     int limit = (int)py_minS((double)S, p + radius + 1);
     b0 = bucket_left / AG_BUCKET;
     b1 = limit > bucket_left ? b0 + (limit - bucket_left - 1) / AG_BUCKET : b0 - 1;

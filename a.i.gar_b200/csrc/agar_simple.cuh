@@ -87,6 +87,16 @@ DEV void s_store(const SReg& r, const SPtr& q) {
     B->stat_frames = r.stat_frames;
 }
 
+/* warp-uniform predicates: every data-dependent loop runs until no lane of the WARP needs another iteration.  Also
+ * for W == 1 — measured: letting 32 single-lane envs leave loops independently is 4x slower (they never reconverge) */
+template <int W>
+DEV bool s_any(bool p) {
+    return __any_sync(S_FULL, p);
+}
+template <int W>
+DEV void s_sync() {
+    __syncwarp();
+}
 template <int W>
 DEV int tile_min(int v) {
 #pragma unroll
@@ -146,7 +156,7 @@ DEV void s_observe(SReg& r, const SPtr& q, const DevParams& P, bool mine, float*
         r.fov_size_feat = P.cfg.use_fovsize ? r.fov_size : r.fov_size_feat;
     }
     const bool out = mine && row != nullptr;
-    if (!__any_sync(S_FULL, out)) return;
+    if (!s_any<W>(out)) return;
     if (out) { /* clear the row; extras: [fov size], [total mass] (bot.py:302-323) */
         for (int i = sub; i < GG; i += W) row[i] = 0.f;
         if (sub == 0) {
@@ -156,7 +166,7 @@ DEV void s_observe(SReg& r, const SPtr& q, const DevParams& P, bool mine, float*
             (void)SL;
         }
     }
-    __syncwarp(); /* orders the clearing stores before the REDs below (same warp) */
+    s_sync<W>(); /* orders the clearing stores before the REDs below (same warp) */
     if (out) {
         const double fov = r.fov_size, fx = r.fov_x, fy = r.fov_y;
         const double left = fx - fov / 2, top = fy - fov / 2;
@@ -176,11 +186,33 @@ DEV void s_observe(SReg& r, const SPtr& q, const DevParams& P, bool mine, float*
         const double xmin = fx - h, xmax = fx + h, ymin = fy - h, ymax = fy + h;
         /* integer window that contains every pellet in_fov() can accept (radius < 1) */
         const int wx0 = (int)floor(xmin) - 1, wx1 = (int)ceil(xmax) + 1, wy0 = (int)floor(ymin) - 1, wy1 = (int)ceil(ymax) + 1;
-        for (int s = sub; s < P.L.pellet_cap; s += W) {
-            uint32_t pk = q.pel[s];
-            int px = AGAR_PELLET_X(pk), py = AGAR_PELLET_Y(pk);
-            if (px < wx0 || px > wx1 || py < wy0 || py > wy1 || pk == 0) continue;
-            int pm = AGAR_PELLET_M(pk);
+        /* phase 1: integer window -> candidate bitmask over this lane's slots (converged, cheap) */
+        unsigned long long m0 = 0, m1 = 0;
+        {
+            int j = 0;
+            for (int s = sub; s < P.L.pellet_cap; s += W, ++j) {
+                uint32_t pk = q.pel[s];
+                int px = AGAR_PELLET_X(pk), py = AGAR_PELLET_Y(pk);
+                if (px >= wx0 && px <= wx1 && py >= wy0 && py <= wy1 && pk != 0) {
+                    if (j < 64)
+                        m0 |= 1ull << j;
+                    else
+                        m1 |= 1ull << (j - 64);
+                }
+            }
+        }
+        /* phase 2: every lane bins its own next candidate per iteration (lanes stay busy until the longest list ends) */
+        while (m0 | m1) {
+            int j;
+            if (m0) {
+                j = __ffsll((long long)m0) - 1;
+                m0 &= m0 - 1;
+            } else {
+                j = 64 + __ffsll((long long)m1) - 1;
+                m1 &= m1 - 1;
+            }
+            uint32_t pk = q.pel[sub + W * j];
+            int px = AGAR_PELLET_X(pk), py = AGAR_PELLET_Y(pk), pm = AGAR_PELLET_M(pk);
             double pr = P.pellet_r[pm & 3];
             double dx = (double)px, dy = (double)py;
             if (!rect_hit(ra, pellet_rect(px, py)) || (dx + pr < xmin || dx - pr > xmax || dy + pr < ymin || dy - pr > ymax))
@@ -224,6 +256,10 @@ DEV void s_field_update(SReg& r, const SPtr& q, const DevParams& P, uint32_t env
     const int icx = (int)cx, icy = (int)cy;
     const int cap = P.L.pellet_cap;
     int reach = (int)radius + 2;
+    /* When the pool is full (the steady state: cap == refill target) the free slots after eating are exactly the
+     * eaten ones, in ascending order — remember up to four and skip the free-slot search when respawning. */
+    const bool pool_full = r.n_pellets == cap;
+    int eaten0 = S_NONE, eaten1 = S_NONE, eaten2 = S_NONE, eaten3 = S_NONE, n_eaten = 0;
     unsigned long long m0 = 0, m1 = 0; /* bit j <-> slot sub + W*j */
     auto scan = [&](int first_slot) {
         m0 = m1 = 0;
@@ -245,7 +281,7 @@ DEV void s_field_update(SReg& r, const SPtr& q, const DevParams& P, uint32_t env
     while (true) {
         int mine = m0 ? sub + W * (__ffsll((long long)m0) - 1) : (m1 ? sub + W * (64 + __ffsll((long long)m1) - 1) : S_NONE);
         int first = tile_min<W>(mine);
-        if (!__any_sync(S_FULL, first != S_NONE)) break;
+        if (!s_any<W>(first != S_NONE)) break;
         if (first != S_NONE && mine == first) { /* owner lane drops the candidate */
             int j = (first - sub) / W;
             if (j < 64)
@@ -254,7 +290,7 @@ DEV void s_field_update(SReg& r, const SPtr& q, const DevParams& P, uint32_t env
                 m1 &= ~(1ull << (j - 64));
         }
         const uint32_t pk = q.pel[first != S_NONE ? first : 0];
-        __syncwarp(); /* every lane has read its tile's candidate before lane sub == 0 may clear the slot */
+        s_sync<W>(); /* every lane has read its tile's candidate before lane sub == 0 may clear the slot */
         if (first != S_NONE) {
             int px = AGAR_PELLET_X(pk), py = AGAR_PELLET_Y(pk), pm = AGAR_PELLET_M(pk);
             if (rect_hit(rc, pellet_rect(px, py)) &&
@@ -266,6 +302,11 @@ DEV void s_field_update(SReg& r, const SPtr& q, const DevParams& P, uint32_t env
                 radius = radius_of(nm);
                 if (sub == 0) q.pel[first] = 0;
                 r.n_pellets -= 1;
+                if (n_eaten == 0) eaten0 = first;
+                else if (n_eaten == 1) eaten1 = first;
+                else if (n_eaten == 2) eaten2 = first;
+                else if (n_eaten == 3) eaten3 = first;
+                n_eaten += 1;
                 if ((int)radius + 2 > reach) { /* the grown cell reaches farther: re-scan the slots after this one */
                     reach = (int)radius + 2;
                     scan(first + 1);
@@ -274,13 +315,17 @@ DEV void s_field_update(SReg& r, const SPtr& q, const DevParams& P, uint32_t env
         }
     }
     r.mass = mass, r.radius = radius;
-    __syncwarp(); /* eaten slots are visible to the tile before the free-slot search */
+    s_sync<W>(); /* eaten slots are visible to the tile before the free-slot search */
     /* spawnPellets (field.py:303-313) */
     int from = 0;
-    while (__any_sync(S_FULL, (double)r.n_pellets < P.L.max_pellets)) {
+    while (s_any<W>((double)r.n_pellets < P.L.max_pellets)) {
         const bool need = (double)r.n_pellets < P.L.max_pellets;
         int mine = S_NONE;
-        if (need) {
+        const bool known = pool_full && n_eaten <= 4;
+        if (need && known) {
+            mine = eaten0; /* the lowest free slot is the earliest eaten one */
+            eaten0 = eaten1, eaten1 = eaten2, eaten2 = eaten3, eaten3 = S_NONE;
+        } else if (need) {
             int s = from + ((sub - from) % W + W) % W; /* first slot >= from owned by this lane */
             for (; s < cap; s += W)
                 if (q.pel[s] == 0) {
@@ -302,7 +347,7 @@ DEV void s_field_update(SReg& r, const SPtr& q, const DevParams& P, uint32_t env
                 from = slot + 1;
             }
         }
-        __syncwarp();
+        s_sync<W>();
     }
     r.frame += 1;
 }

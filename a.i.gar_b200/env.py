@@ -11,7 +11,7 @@ import numpy as np
 from . import layout as lay
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libagar_b200.so")
+_LIB_PATH = os.environ.get("AGAR_B200_LIB", os.path.join(_HERE, "libagar_b200.so"))  # override: A/B builds
 _lib = None
 
 EXPORTS = ["agar_layout_for_config", "agar_create", "agar_destroy", "agar_last_error", "agar_get_layout", "agar_num_envs",
