@@ -170,7 +170,7 @@ DEV void s_observe(SReg& r, const SPtr& q, const DevParams& P, bool mine, float*
     if (out) {
         const double fov = r.fov_size, fx = r.fov_x, fy = r.fov_y;
         const double left = fx - fov / 2, top = fy - fov / 2;
-        const double gs = fov / G;
+        const double gs = fov / G, inv = 1.0 / gs;
         const int cols = P.cfg.obs_mode == AGAR_OBS_CANONICAL ? G : (int)ceil(fov / gs);
         /* squares entirely outside the field show nothing (bot.py:392-393); mid points accumulate like the reference */
         double mx = left + gs / 2, my = top + gs / 2;
@@ -218,7 +218,7 @@ DEV void s_observe(SReg& r, const SPtr& q, const DevParams& P, bool mine, float*
             if (!rect_hit(ra, pellet_rect(px, py)) || (dx + pr < xmin || dx - pr > xmax || dy + pr < ymin || dy - pr > ymax))
                 continue;
             float fm = (float)pm;
-            for_each_fov_bucket(dx, dy, pr, left, top, fov, gs, cols, [&](int id) {
+            for_each_fov_bucket(dx, dy, pr, left, top, fov, gs, inv, cols, [&](int id) {
                 if (id < GG) { /* bucket `id` is read by square (id / G, id % G): the reference's shear when cols == G+1 */
                     int cc = id / G, rr = id - cc * G;
                     if (!((row_bad >> cc & 1) || (col_bad >> rr & 1))) atomicAdd(&row[id], fm);

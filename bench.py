@@ -319,7 +319,7 @@ def main():
     launch_ms = total_ms / args.steps
     achieved = E * frames * bytes_per / (launch_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": profiled_traffic(E, frames), "kernel": "k_main<W,false>", "peak_source": peak_src,
+                "traffic": profiled_traffic(E, frames), "kernel": ("k_simple<%d>" if batch.tile_width <= 16 else "k_main<%d,false>") % batch.tile_width, "peak_source": peak_src,
                 "bytes_per_env_step": bytes_per, "env_steps_per_launch": E * frames, "launch_ms": launch_ms}
     cpu = None
     if world == 1 and not args.no_cpu:
