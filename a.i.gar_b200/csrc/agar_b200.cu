@@ -391,7 +391,8 @@ static int launch_main(AgarEnv* e, const float* actions, float* obs, int n_frame
         else if (e->simple_W == 2) LAUNCH_SIMPLE(2);
         else if (e->simple_W == 4) LAUNCH_SIMPLE(4);
         else if (e->simple_W == 8) LAUNCH_SIMPLE(8);
-        else LAUNCH_SIMPLE(16);
+        else if (e->simple_W == 16) LAUNCH_SIMPLE(16);
+        else LAUNCH_SIMPLE(32);
 #undef LAUNCH_SIMPLE
     } else
         err = DISPATCH(launch_main_t, e, actions, obs, n_frames, n_dec, flags, dec_base, (cudaStream_t)stream);
@@ -414,7 +415,7 @@ static int launch_init(AgarEnv* e, const uint8_t* mask, int mode, void* stream) 
  * (agar_simple.cuh), 16 / 32 the general kernel; every other config: 4, 8, 16, 32 (general kernel). */
 extern "C" int agar_set_tile_width(AgarEnv* e, int W) {
     if (!e) return AGAR_E_INVALID;
-    if (!e->full && (W == 1 || W == 2 || W == 4 || W == 8 || W == 16)) {
+    if (!e->full && (W == 1 || W == 2 || W == 4 || W == 8 || W == 16 || W == 32) && !getenv("AGAR_GENERAL_KERNEL")) {
         int tail_words = (int)((e->L.record_bytes - e->L.off_pellets) / 4);
         e->sp.strideB = (tail_words | 1) * 4;
         if (e->L.pellet_cap > 128 * W) return fail(e, AGAR_E_UNSUPPORTED, "pellet pool too large for this tile width%s", "");
