@@ -40,10 +40,11 @@ __device__ __forceinline__ void stage_out(const DevParams& P, uint8_t* state, in
     }
 }
 template <int W>
-__device__ __forceinline__ void bind_ctx(Ctx<W>& c, const DevParams& P, int tile_id, int tiles, int env) {
+__device__ __forceinline__ void bind_ctx(Ctx<W>& c, const DevParams& P, int tile_id, int tiles, int env, uint8_t* state) {
     c.lane = c.t.thread_rank();
     c.env_id = (uint32_t)(P.first_env + (uint64_t)env);
-    c.rec = g_smem + (size_t)tile_id * P.rec_stride;
+    c.rec = P.stage ? g_smem + (size_t)tile_id * P.rec_stride : nullptr;
+    if (!P.stage) c.rec = state + (size_t)env * P.L.record_bytes; /* big records: step in place, through L1 / L2 */
     c.h = (AgarEnvHeader*)(c.rec + P.L.off_header);
     c.pl = (AgarPlayer*)(c.rec + P.L.off_players);
     c.cells = (AgarCell*)(c.rec + P.L.off_cells);
@@ -53,7 +54,7 @@ __device__ __forceinline__ void bind_ctx(Ctx<W>& c, const DevParams& P, int tile
     c.pel = (uint32_t*)(c.rec + P.L.off_pellets);
     c.hist = (float*)(c.rec + P.L.off_hist);
     c.ev = (AgarEvent*)(c.rec + P.L.off_events);
-    c.scratch = g_smem + (size_t)tiles * P.rec_stride + (size_t)tile_id * P.scratch_bytes;
+    c.scratch = g_smem + (P.stage ? (size_t)tiles * P.rec_stride : 0) + (size_t)tile_id * P.scratch_bytes;
 }
 
 /* ------------------------------------------------------------------ the step kernel */
@@ -64,12 +65,12 @@ k_main(const __grid_constant__ DevParams P, uint8_t* __restrict__ state, const f
     const int tiles = blockDim.x / W;
     const int env0 = blockIdx.x * tiles;
     const int n_here = min(tiles, P.n_envs - env0);
-    stage_in(P, state, env0, n_here, false);
+    if (P.stage) stage_in(P, state, env0, n_here, false);
     const int tile_id = threadIdx.x / W;
     if (tile_id < n_here) {
         Ctx<W> c(cg::tiled_partition<W>(cg::this_thread_block()));
         const int env = env0 + tile_id;
-        bind_ctx(c, P, tile_id, tiles, env);
+        bind_ctx(c, P, tile_id, tiles, env, state);
         const int A = P.L.n_agents, K = P.L.n_players, SL = P.L.state_len;
         float* obs_env = obs ? obs + (size_t)env * A * SL : nullptr;
         for (int d = 0; d < n_dec; ++d) {
@@ -108,7 +109,7 @@ k_main(const __grid_constant__ DevParams P, uint8_t* __restrict__ state, const f
         if (flags & KF_OBS_AFTER)
             for (int a = 0; a < A; ++a) nn_turn_begin<W, FULL>(c, P, a, obs_env ? obs_env + (size_t)a * SL : nullptr);
     }
-    stage_out(P, state, env0, n_here);
+    if (P.stage) stage_out(P, state, env0, n_here);
 }
 
 
@@ -197,11 +198,18 @@ k_init(const __grid_constant__ DevParams P, uint8_t* __restrict__ state, const u
     const int tiles = blockDim.x / W;
     const int env0 = blockIdx.x * tiles;
     const int n_here = min(tiles, P.n_envs - env0);
-    stage_in(P, state, env0, n_here, mode == 0);
+    if (P.stage)
+        stage_in(P, state, env0, n_here, mode == 0);
+    else if (mode == 0) { /* records stay in HBM: clear them in place */
+        const int chunks = (int)(P.L.record_bytes / 8);
+        uint2* dst = (uint2*)(state + (size_t)env0 * P.L.record_bytes);
+        for (int i = threadIdx.x; i < n_here * chunks; i += blockDim.x) dst[i] = make_uint2(0u, 0u);
+        __syncthreads();
+    }
     const int tile_id = threadIdx.x / W;
     if (tile_id < n_here && (mask == nullptr || mode == 0 || mask[env0 + tile_id])) {
         Ctx<W> c(cg::tiled_partition<W>(cg::this_thread_block()));
-        bind_ctx(c, P, tile_id, tiles, env0 + tile_id);
+        bind_ctx(c, P, tile_id, tiles, env0 + tile_id, state);
         const int K = P.L.n_players;
         if (mode == 0 || mode == 1) {
             if (mode == 1) { /* clear pools cooperatively: fresh lists and hash tables */
@@ -249,7 +257,7 @@ k_init(const __grid_constant__ DevParams P, uint8_t* __restrict__ state, const u
             c.t.sync();
         }
     }
-    stage_out(P, state, env0, n_here);
+    if (P.stage) stage_out(P, state, env0, n_here);
 }
 
 /* agar_get: one thread per (env, agent) or per env, straight from HBM */
@@ -335,7 +343,7 @@ static bool config_is_simple(const AgarConfig& c, const AgarLayout& L) {
 /* pick the launch shape for tile width W; returns false if one record does not fit in shared memory */
 static bool plan_launch(AgarEnv* e, int W) {
     const size_t budget = 200 * 1024;
-    size_t per_tile = (size_t)e->P.rec_stride + (size_t)e->P.scratch_bytes;
+    size_t per_tile = (e->P.stage ? (size_t)e->P.rec_stride : 0) + (size_t)e->P.scratch_bytes;
     int tiles = 128 / W;
     while (tiles > 1 && per_tile * tiles > budget) tiles >>= 1;
     if (per_tile * tiles > budget) return false;
@@ -467,6 +475,10 @@ extern "C" int agar_create(const AgarConfig* cfg, int n_envs, int device, uint64
     P.n_envs = n_envs;
     P.rec_stride = (int)L.record_bytes + 8;
     P.full = e->full;
+    /* small records are stepped in shared memory; big ones (multi-agent arenas: 60 KB) in place through L1 / L2,
+     * which keeps >= 32 warps per SM resident instead of 3 (profiles/r01_sweep_full.txt) */
+    P.stage = L.record_bytes <= 16 * 1024;
+    if (getenv("AGAR_STAGE")) P.stage = atoi(getenv("AGAR_STAGE")) != 0;
     int vel_bytes = e->full ? L.n_players * L.cell_cap * 2 * 8 : 0;
     int obs_bytes = obs_scratch_bytes(L.grid_squares, e->full != 0);
     P.scratch_bytes = ((vel_bytes > obs_bytes ? vel_bytes : obs_bytes) + 15) / 16 * 16 + 8;

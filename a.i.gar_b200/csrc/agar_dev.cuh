@@ -38,7 +38,7 @@ struct DevParams {
     AgarConfig cfg;
     AgarLayout L;
     int S, nb, n_envs, rec_stride; /* rec_stride: bytes between staged records in shared memory */
-    int scratch_bytes, full, pad0, pad1;
+    int scratch_bytes, full, stage, pad1; /* stage: 1 = records live in shared memory during a launch, 0 = in HBM/L2 */
     double move_speed, decay_rate, blob_mass, virus_split_mass, start_radius, virus_radius;
     double pellet_r[4];
     double pow_n[17];
