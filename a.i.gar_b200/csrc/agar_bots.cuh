@@ -131,10 +131,14 @@ DEV void observe_agent(Ctx<W>& c, const DevParams& P, int k, int agent, float* o
     c.t.sync();
     const Rect ra = rect_of(P.S, fx, fy, fov / 2);
     /* integer pellets (field.getPelletsInFov -> insertAllFloatingPointObjects): integer adds commute */
+    /* integer window that contains every pellet in_fov() can accept (radius < 1) */
+    const int wx0 = (int)floor(fx - fov / 2) - 1, wx1 = (int)ceil(fx + fov / 2) + 1;
+    const int wy0 = (int)floor(fy - fov / 2) - 1, wy1 = (int)ceil(fy + fov / 2) + 1;
     for (int s = c.lane; s < P.L.pellet_cap; s += W) {
         uint32_t pk = c.pel[s];
-        if (!pk) continue;
-        int px = AGAR_PELLET_X(pk), py = AGAR_PELLET_Y(pk), pm = AGAR_PELLET_M(pk);
+        int px = AGAR_PELLET_X(pk), py = AGAR_PELLET_Y(pk);
+        if (px < wx0 || px > wx1 || py < wy0 || py > wy1 || !pk) continue;
+        int pm = AGAR_PELLET_M(pk);
         double pr = P.pellet_r[pm & 3];
         if (!rect_hit(ra, pellet_rect(px, py)) || !in_fov((double)px, (double)py, pr, fx, fy, fov)) continue;
         for_each_fov_bucket((double)px, (double)py, pr, left, top, fov, gs, inv, cols,
@@ -406,10 +410,13 @@ DEV void scripted_turn(Ctx<W>& c, const DevParams& P, int k) {
             if (key > best || (key == best && ord < best_ord)) best = key, bestx = ox, besty = oy, best_ord = ord;
         };
         int ord0 = 0;
+        const int wx0 = (int)floor(fx - fov / 2) - 1, wx1 = (int)ceil(fx + fov / 2) + 1;
+        const int wy0 = (int)floor(fy - fov / 2) - 1, wy1 = (int)ceil(fy + fov / 2) + 1;
         for (int s = c.lane; s < P.L.pellet_cap; s += W) {
             uint32_t pk = c.pel[s];
-            if (!pk) continue;
-            int px = AGAR_PELLET_X(pk), py = AGAR_PELLET_Y(pk), pm = AGAR_PELLET_M(pk);
+            int px = AGAR_PELLET_X(pk), py = AGAR_PELLET_Y(pk);
+            if (px < wx0 || px > wx1 || py < wy0 || py > wy1 || !pk) continue; /* integer FOV window first */
+            int pm = AGAR_PELLET_M(pk);
             double pr = P.pellet_r[pm & 3];
             if (!rect_hit(ra, pellet_rect(px, py)) || !in_fov((double)px, (double)py, pr, fx, fy, fov)) continue;
             consider((double)px, (double)py, (double)pm, ord0 + s);

@@ -826,13 +826,22 @@ DEV void cell_eats_pellets(Ctx<W>& c, const DevParams& P, int k, int ci, bool fa
     double cx = q->x, cy = q->y, cm = q->mass, cr = q->radius;
     const Rect rc = rect_of(P.S, cx, cy, cr); /* candidates are fixed before the cell grows */
     const int cap = P.L.pellet_cap;
-    /* conservative integer window: nothing farther than the largest radius this cell can reach this frame
-     * matters.  Not used for correctness, only the exact tests below are. */
+    /* Integer window: a pellet can only be eaten if it lies within the cell's radius, and within one chunk of W
+     * pellets the cell gains at most 3 W mass — so nothing outside |d| <= radius(mass + 3 W) + 2 matters for the
+     * chunk at hand.  The window only skips chunks; hits are decided by the exact tests below.  It is
+     * re-derived after every eat. */
+    const int icx = (int)cx, icy = (int)cy;
+    const bool windowed = cap > 8 * W; /* small pools: the window costs more than the chunks it skips (measured) */
+    int reach = windowed ? (int)sqrt((cm + 3.0 * W) / M_PI) + 2 : 4096;
     for (int base = 0; base < cap; base += W) {
         int s = base + c.lane;
         uint32_t pk = s < cap ? c.pel[s] : 0u;
-        int px = AGAR_PELLET_X(pk), py = AGAR_PELLET_Y(pk), pm = AGAR_PELLET_M(pk);
-        bool cand = pk != 0 && rect_hit(rc, pellet_rect(px, py));
+        int px = AGAR_PELLET_X(pk), py = AGAR_PELLET_Y(pk);
+        bool win = pk != 0 && (unsigned)(px - icx + reach) <= (unsigned)(2 * reach) &&
+                   (unsigned)(py - icy + reach) <= (unsigned)(2 * reach);
+        if (windowed && !c.t.any(win)) continue;
+        int pm = AGAR_PELLET_M(pk);
+        bool cand = win && rect_hit(rc, pellet_rect(px, py));
         double pr = P.pellet_r[pm & 3];
         unsigned done_mask = 0; /* lanes at or below the last eaten one */
         while (true) {
@@ -852,6 +861,7 @@ DEV void cell_eats_pellets(Ctx<W>& c, const DevParams& P, int k, int ci, bool fa
                 c.h->n_pellets -= 1;
             }
             done_mask |= (l == 31) ? 0xffffffffu : ((2u << l) - 1);
+            if (windowed) reach = (int)sqrt((cm + 3.0 * W) / M_PI) + 2;
         }
     }
     if (fat_too) {

@@ -306,6 +306,26 @@ def main():
             b2.close()
         except Exception as ex:  # never lose the headline line to the side measurement
             extra["envs_262144"] = {"error": str(ex)[:200]}
+        try:  # BASELINE configs[4] shard: obs -> DLPack -> torch DQN forward -> arg-max -> 5x5 table -> 8 frames
+            from aigar_b200.dqn import DQNDriver
+            E3, ticks = 65536, 20
+            b3 = AgarBatch(cfg, E3, device=local, seed=2026, first_env_id=2 * 10 ** 6)
+            drv = DQNDriver(b3, seed=0)
+            drv.run(5)
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(ticks):
+                drv.tick()
+            e.record()
+            torch.cuda.synchronize()
+            ms = s.elapsed_time(e)
+            extra["dqn_65536"] = {"value": E3 * ticks * PERIOD / (ms * 1e-3), "unit": UNIT, "ms_per_tick": ms / ticks,
+                                  "policy": "torch MLP 123-100-100-25 (fp32), arg-max, 5x5 action table; obs via DLPack",
+                                  "tile_width": b3.tile_width}
+            b3.close()
+        except Exception as ex:
+            extra["dqn_65536"] = {"error": str(ex)[:200]}
 
     if dist is not None:
         dist.barrier()

