@@ -77,6 +77,31 @@ DEV unsigned axis_buckets(double p, double radius, double fov, double gs, double
     }
     return m;
 }
+/* int(x / gs) for x within a few ulp of a multiple of gs — the exact-residual test of axis_buckets, branch-light */
+DEV int bucket_of_edge(double x, double gs, double inv) {
+    double k = rint(x * inv);
+    int col = (int)k;
+    double rho = fma(k, gs, -x);
+    uint64_t kb = agar_double_to_bits(k);
+    int e = (int)((kb >> 52) & 0x7ff);
+    int pow2 = (kb & 0x000fffffffffffffULL) == 0;
+    double thr = gs * agar_bits_to_double((uint64_t)(e - 53 - pow2) << 52);
+    return (col > 0 && rho > thr) ? col - 1 : col;
+}
+/* axis_buckets for objects with 2 * radius < gs (every integer pellet: radius < 1, gs > 2.3 for G <= 16): the
+ * reference loop visits x0 = bucketLeft and at most x1 = x0 + gs.  Straight-line, so a warp stays converged.
+ * Returns the two bucket indices (or -1) instead of a mask. */
+DEV void axis_buckets2(double p, double radius, double fov, double gs, double inv, int& b0, int& b1) {
+    double cl = py_max0(p - radius);
+    double q = floor(cl * inv);
+    double res = fma(-q, gs, cl);
+    q = res < 0 ? q - 1 : (res >= gs ? q + 1 : q);
+    const double x0 = q * gs, x1 = x0 + gs;
+    const double lim = (p + radius < fov - 1) ? p + radius : fov - 1;
+    int c0 = bucket_of_edge(x0, gs, inv), c1 = bucket_of_edge(x1, gs, inv);
+    b0 = x0 <= lim ? c0 : -1;
+    b1 = (x1 <= lim && c1 != c0) ? c1 : -1; /* ids is a set */
+}
 /* calls f(id) once per distinct bucket of the object (ids is a set in the reference) */
 template <class F>
 DEV void for_each_fov_bucket(double ox, double oy, double radius, double left, double top, double fov, double gs,

@@ -189,19 +189,24 @@ DEV void s_observe(SReg& r, const SPtr& q, const DevParams& P, bool mine, float*
         /* phase 1: integer window -> candidate bitmask over this lane's slots (converged, cheap) */
         unsigned long long m0 = 0, m1 = 0;
         {
+            const int cap = P.L.pellet_cap, split = min(cap, sub + 64 * W);
             int j = 0;
-            for (int s = sub; s < P.L.pellet_cap; s += W, ++j) {
+            for (int s = sub; s < split; s += W, ++j) { /* branch-free accumulation, two plain loops */
                 uint32_t pk = q.pel[s];
                 int px = AGAR_PELLET_X(pk), py = AGAR_PELLET_Y(pk);
-                if (px >= wx0 && px <= wx1 && py >= wy0 && py <= wy1 && pk != 0) {
-                    if (j < 64)
-                        m0 |= 1ull << j;
-                    else
-                        m1 |= 1ull << (j - 64);
-                }
+                bool in = px >= wx0 && px <= wx1 && py >= wy0 && py <= wy1 && pk != 0;
+                m0 |= (unsigned long long)in << j;
+            }
+            j = 0;
+            for (int s = sub + 64 * W; s < cap; s += W, ++j) {
+                uint32_t pk = q.pel[s];
+                int px = AGAR_PELLET_X(pk), py = AGAR_PELLET_Y(pk);
+                bool in = px >= wx0 && px <= wx1 && py >= wy0 && py <= wy1 && pk != 0;
+                m1 |= (unsigned long long)in << j;
             }
         }
-        /* phase 2: every lane bins its own next candidate per iteration (lanes stay busy until the longest list ends) */
+        /* phase 2: every lane bins its own next candidate per iteration.  The body is straight-line (predicated REDs,
+         * two-bucket axis form), so the lanes of a warp stay converged until the longest list ends. */
         while (m0 | m1) {
             int j;
             if (m0) {
@@ -215,15 +220,20 @@ DEV void s_observe(SReg& r, const SPtr& q, const DevParams& P, bool mine, float*
             int px = AGAR_PELLET_X(pk), py = AGAR_PELLET_Y(pk), pm = AGAR_PELLET_M(pk);
             double pr = P.pellet_r[pm & 3];
             double dx = (double)px, dy = (double)py;
-            if (!rect_hit(ra, pellet_rect(px, py)) || (dx + pr < xmin || dx - pr > xmax || dy + pr < ymin || dy - pr > ymax))
-                continue;
+            bool ok = rect_hit(ra, pellet_rect(px, py)) && !(dx + pr < xmin || dx - pr > xmax || dy + pr < ymin || dy - pr > ymax);
+            int c0, c1, r0, r1;
+            axis_buckets2(dx - left, pr, fov, gs, inv, c0, c1);
+            axis_buckets2(dy - top, pr, fov, gs, inv, r0, r1);
             float fm = (float)pm;
-            for_each_fov_bucket(dx, dy, pr, left, top, fov, gs, inv, cols, [&](int id) {
-                if (id < GG) { /* bucket `id` is read by square (id / G, id % G): the reference's shear when cols == G+1 */
-                    int cc = id / G, rr = id - cc * G;
-                    if (!((row_bad >> cc & 1) || (col_bad >> rr & 1))) atomicAdd(&row[id], fm);
-                }
-            });
+            auto put = [&](int cc, int rr) {
+                int id = cc + rr * cols; /* bucket id; square (id / G, id % G) reads it: the shear when cols == G + 1 */
+                int sc = id / G, sr = id - sc * G;
+                if (ok && cc >= 0 && rr >= 0 && id < GG && !((row_bad >> sc & 1) || (col_bad >> sr & 1))) atomicAdd(&row[id], fm);
+            };
+            put(c0, r0);
+            put(c1, r0);
+            put(c0, r1);
+            put(c1, r1);
         }
     }
 }
@@ -263,18 +273,21 @@ DEV void s_field_update(SReg& r, const SPtr& q, const DevParams& P, uint32_t env
     unsigned long long m0 = 0, m1 = 0; /* bit j <-> slot sub + W*j */
     auto scan = [&](int first_slot) {
         m0 = m1 = 0;
+        const int split = min(cap, sub + 64 * W);
+        const unsigned r2 = (unsigned)(2 * reach);
         int j = 0;
-        for (int s = sub; s < cap; s += W, ++j) {
+        for (int s = sub; s < split; s += W, ++j) { /* branch-free accumulation, two plain loops */
             uint32_t pk = q.pel[s];
             int px = AGAR_PELLET_X(pk), py = AGAR_PELLET_Y(pk);
-            bool in = (unsigned)(px - icx + reach) <= (unsigned)(2 * reach) && (unsigned)(py - icy + reach) <= (unsigned)(2 * reach) &&
-                      pk != 0 && s >= first_slot;
-            if (in) {
-                if (j < 64)
-                    m0 |= 1ull << j;
-                else
-                    m1 |= 1ull << (j - 64);
-            }
+            bool in = (unsigned)(px - icx + reach) <= r2 && (unsigned)(py - icy + reach) <= r2 && pk != 0 && s >= first_slot;
+            m0 |= (unsigned long long)in << j;
+        }
+        j = 0;
+        for (int s = sub + 64 * W; s < cap; s += W, ++j) {
+            uint32_t pk = q.pel[s];
+            int px = AGAR_PELLET_X(pk), py = AGAR_PELLET_Y(pk);
+            bool in = (unsigned)(px - icx + reach) <= r2 && (unsigned)(py - icy + reach) <= r2 && pk != 0 && s >= first_slot;
+            m1 |= (unsigned long long)in << j;
         }
     };
     scan(0);
