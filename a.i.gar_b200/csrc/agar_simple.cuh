@@ -207,6 +207,7 @@ DEV void s_observe(SReg& r, const SPtr& q, const DevParams& P, bool mine, float*
         }
         /* phase 2: every lane bins its own next candidate per iteration.  The body is straight-line (predicated REDs,
          * two-bucket axis form), so the lanes of a warp stay converged until the longest list ends. */
+        const bool sheared = cols != G;
         while (m0 | m1) {
             int j;
             if (m0) {
@@ -226,9 +227,12 @@ DEV void s_observe(SReg& r, const SPtr& q, const DevParams& P, bool mine, float*
             axis_buckets2(dy - top, pr, fov, gs, inv, r0, r1);
             float fm = (float)pm;
             auto put = [&](int cc, int rr) {
-                int id = cc + rr * cols; /* bucket id; square (id / G, id % G) reads it: the shear when cols == G + 1 */
-                int sc = id / G, sr = id - sc * G;
-                if (ok && cc >= 0 && rr >= 0 && id < GG && !((row_bad >> sc & 1) || (col_bad >> sr & 1))) atomicAdd(&row[id], fm);
+                /* bucket id = cc + rr * cols is read by square (id / G, id % G).  cols == G: that is (rr, cc); cols == G + 1
+                 * (the reference's shear): id = (cc + rr) + rr * G — no integer division either way */
+                int sr = sheared ? cc + rr : cc, sc = rr;
+                if (sr >= G) sr -= G, sc += 1;
+                int id = sr + sc * G;
+                if (ok && cc >= 0 && rr >= 0 && sc < G && !((row_bad >> sc & 1) || (col_bad >> sr & 1))) atomicAdd(&row[id], fm);
             };
             put(c0, r0);
             put(c1, r0);
