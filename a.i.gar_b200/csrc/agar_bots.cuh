@@ -48,7 +48,21 @@ DEV ObsScratch obs_scratch(uint8_t* base, int G, bool full) {
  *   residual rho = k*gs - x (one fma), that happens iff rho > half_gap_below(k) * gs (a tie rounds to k: even).
  * inv = 1 / gs is only used for estimates that the exact residuals then settle.  Checked against the plain
  * formula on 6e7 adversarial inputs on the host and end to end by the GPU parity tests. */
-DEV unsigned axis_buckets(double p, double radius, double fov, double gs, double inv) {
+/* mathematically exact floor(v / gs), v >= 0 (estimate from the reciprocal, settled by one exact fma residual) */
+DEV int exact_floor_div(double v, double gs, double inv) {
+    double q = floor(v * inv);
+    double res = fma(-q, gs, v);
+    q = res < 0 ? q - 1 : (res >= gs ? q + 1 : q);
+    return (int)q;
+}
+DEV unsigned axis_buckets(double p, double radius, double fov, double gs, double inv, bool canon) {
+    if (canon) { /* AGAR_OBS_CANONICAL: buckets floor(lo / gs) .. floor(hi / gs) with exact floors */
+        double lo = py_max0(p - radius), hi = (p + radius < fov - 1) ? p + radius : fov - 1;
+        if (hi < 0) return 0u;
+        int b0 = exact_floor_div(lo, gs, inv), b1 = exact_floor_div(hi, gs, inv);
+        if (b1 < b0) return 0u;
+        return (b1 >= 31 ? 0xffffffffu : ((2u << b1) - 1)) & ~((1u << b0) - 1);
+    }
     double cl = py_max0(p - radius);
     double q = floor(cl * inv);
     double res = fma(-q, gs, cl);
@@ -91,7 +105,14 @@ DEV int bucket_of_edge(double x, double gs, double inv) {
 /* axis_buckets for objects with 2 * radius < gs (every integer pellet: radius < 1, gs > 2.3 for G <= 16): the
  * reference loop visits x0 = bucketLeft and at most x1 = x0 + gs.  Straight-line, so a warp stays converged.
  * Returns the two bucket indices (or -1) instead of a mask. */
-DEV void axis_buckets2(double p, double radius, double fov, double gs, double inv, int& b0, int& b1) {
+DEV void axis_buckets2(double p, double radius, double fov, double gs, double inv, bool canon, int& b0, int& b1) {
+    if (canon) {
+        double lo = py_max0(p - radius), hi = (p + radius < fov - 1) ? p + radius : fov - 1;
+        int c0 = exact_floor_div(lo, gs, inv), c1 = hi >= 0 ? exact_floor_div(py_max0(hi), gs, inv) : -1;
+        b0 = c1 >= c0 ? c0 : -1;
+        b1 = c1 > c0 ? c1 : -1; /* 2 * radius < gs: at most two buckets */
+        return;
+    }
     double cl = py_max0(p - radius);
     double q = floor(cl * inv);
     double res = fma(-q, gs, cl);
@@ -105,9 +126,9 @@ DEV void axis_buckets2(double p, double radius, double fov, double gs, double in
 /* calls f(id) once per distinct bucket of the object (ids is a set in the reference) */
 template <class F>
 DEV void for_each_fov_bucket(double ox, double oy, double radius, double left, double top, double fov, double gs,
-                             double inv, int cols, F f) {
-    unsigned mx = axis_buckets(ox - left, radius, fov, gs, inv);
-    const unsigned my = axis_buckets(oy - top, radius, fov, gs, inv);
+                             double inv, int cols, bool canon, F f) {
+    unsigned mx = axis_buckets(ox - left, radius, fov, gs, inv, canon);
+    const unsigned my = axis_buckets(oy - top, radius, fov, gs, inv, canon);
     while (mx) {
         int col = __ffs(mx) - 1;
         mx &= mx - 1;
@@ -132,7 +153,8 @@ DEV void observe_agent(Ctx<W>& c, const DevParams& P, int k, int agent, float* o
     const double fov = p->fov_size, fx = p->fov_x, fy = p->fov_y;
     const double left = fx - fov / 2, top = fy - fov / 2;
     const double gs = fov / G, inv = 1.0 / gs;
-    const int cols = cf.obs_mode == AGAR_OBS_CANONICAL ? G : (int)ceil(fov / gs); /* spatialHashTable.py:19 */
+    const bool canon = cf.obs_mode == AGAR_OBS_CANONICAL;
+    const int cols = canon ? G : (int)ceil(fov / gs); /* spatialHashTable.py:19 */
     const int nbk = cols * cols;
     ObsScratch sc = obs_scratch(c.scratch, G, FULL);
     for (int i = c.lane; i < nbk; i += W) {
@@ -166,7 +188,7 @@ DEV void observe_agent(Ctx<W>& c, const DevParams& P, int k, int agent, float* o
         int pm = AGAR_PELLET_M(pk);
         double pr = P.pellet_r[pm & 3];
         if (!rect_hit(ra, pellet_rect(px, py)) || !in_fov((double)px, (double)py, pr, fx, fy, fov)) continue;
-        for_each_fov_bucket((double)px, (double)py, pr, left, top, fov, gs, inv, cols,
+        for_each_fov_bucket((double)px, (double)py, pr, left, top, fov, gs, inv, cols, canon,
                             [&](int id) { atomicAdd(&sc.pel_i[id], pm); });
     }
     if (FULL) {
@@ -185,7 +207,7 @@ DEV void observe_agent(Ctx<W>& c, const DevParams& P, int k, int agent, float* o
             }
             unsigned long long* grid = (unsigned long long*)(k2 == k ? sc.own : sc.enemy);
             unsigned long long bits = (unsigned long long)__double_as_longlong(o->mass);
-            for_each_fov_bucket(o->x, o->y, o->radius, left, top, fov, gs, inv, cols,
+            for_each_fov_bucket(o->x, o->y, o->radius, left, top, fov, gs, inv, cols, canon,
                                 [&](int id) { atomicMax(&grid[id], bits); });
         }
     }
@@ -202,7 +224,7 @@ DEV void observe_agent(Ctx<W>& c, const DevParams& P, int k, int agent, float* o
                     if (!rect_hit(ra, rect_of(P.S, f->x, f->y, f->radius)) || !in_fov(f->x, f->y, f->radius, fx, fy, fov))
                         continue;
                     double fm = f->mass;
-                    for_each_fov_bucket(f->x, f->y, f->radius, left, top, fov, gs, inv, cols,
+                    for_each_fov_bucket(f->x, f->y, f->radius, left, top, fov, gs, inv, cols, canon,
                                         [&](int id) { sc.dsum[id] = sc.dsum[id] + fm; });
                 }
             if (cf.virus_enabled) /* mass of the first virus with the largest radius (bot.py:436-441) */
@@ -212,7 +234,7 @@ DEV void observe_agent(Ctx<W>& c, const DevParams& P, int k, int agent, float* o
                         !in_fov(o->x, o->y, o->radius, fx, fy, fov))
                         continue;
                     double orr = o->radius, om = o->mass;
-                    for_each_fov_bucket(o->x, o->y, o->radius, left, top, fov, gs, inv, cols, [&](int id) {
+                    for_each_fov_bucket(o->x, o->y, o->radius, left, top, fov, gs, inv, cols, canon, [&](int id) {
                         if (orr > sc.vir_r[id]) sc.vir_r[id] = orr, sc.vir_m[id] = om;
                     });
                 }

@@ -171,7 +171,8 @@ DEV void s_observe(SReg& r, const SPtr& q, const DevParams& P, bool mine, float*
         const double fov = r.fov_size, fx = r.fov_x, fy = r.fov_y;
         const double left = fx - fov / 2, top = fy - fov / 2;
         const double gs = fov / G, inv = 1.0 / gs;
-        const int cols = P.cfg.obs_mode == AGAR_OBS_CANONICAL ? G : (int)ceil(fov / gs);
+        const bool canon = P.cfg.obs_mode == AGAR_OBS_CANONICAL;
+        const int cols = canon ? G : (int)ceil(fov / gs);
         /* squares entirely outside the field show nothing (bot.py:392-393); mid points accumulate like the reference */
         double mx = left + gs / 2, my = top + gs / 2;
         unsigned col_bad = 0, row_bad = 0;
@@ -223,8 +224,8 @@ DEV void s_observe(SReg& r, const SPtr& q, const DevParams& P, bool mine, float*
             double dx = (double)px, dy = (double)py;
             bool ok = rect_hit(ra, pellet_rect(px, py)) && !(dx + pr < xmin || dx - pr > xmax || dy + pr < ymin || dy - pr > ymax);
             int c0, c1, r0, r1;
-            axis_buckets2(dx - left, pr, fov, gs, inv, c0, c1);
-            axis_buckets2(dy - top, pr, fov, gs, inv, r0, r1);
+            axis_buckets2(dx - left, pr, fov, gs, inv, canon, c0, c1);
+            axis_buckets2(dy - top, pr, fov, gs, inv, canon, r0, r1);
             float fm = (float)pm;
             auto put = [&](int cc, int rr) {
                 /* bucket id = cc + rr * cols is read by square (id / G, id % G).  cols == G: that is (rr, cc); cols == G + 1

@@ -831,7 +831,7 @@ static int in_fov(double x, double y, double r, double fx, double fy, double fov
 
 /* ------------------------------------------------------------------ grid vision (bot.py:326-497, spatialHashTable.py:85-112) */
 typedef struct GridTables {
-    int cols;
+    int cols, canonical;
     double pel_sum[1100];
     double own_max[1100], enemy_max[1100], vir_best_r[1100], vir_mass[1100];
     uint8_t pel_has[1100], own_has[1100], enemy_has[1100], vir_has[1100];
@@ -839,6 +839,16 @@ typedef struct GridTables {
     int serial;
 } GridTables;
 enum { T_PELLET, T_OWN, T_ENEMY, T_VIRUS };
+/* mathematically exact floor(v / gs) for v >= 0 (AGAR_OBS_CANONICAL binning) */
+static int exact_floor_div(double v, double gs) {
+    double q = floor(v / gs);
+    double res = fma(-q, gs, v);
+    if (res < 0)
+        q -= 1;
+    else if (res >= gs)
+        q += 1;
+    return (int)q;
+}
 static void grid_insert(GridTables* g, int table, double ox, double oy, double radius, double mass, double left,
                         double top, double fov, double gs) {
     /* getIdsForAreaFloatingPoint */
@@ -848,9 +858,19 @@ static void grid_insert(GridTables* g, int table, double ox, double oy, double r
     double lx = (px + radius < fov - 1) ? px + radius : fov - 1; /* min(size - 1, pos + radius) */
     double ly = (py + radius < fov - 1) ? py + radius : fov - 1;
     g->serial += 1;
+    int canon = g->canonical;
+    int cx0 = 0, cx1 = -1, cy0 = 0, cy1 = -1;
+    if (canon) { /* robust mode: the buckets floor(lo / gs) .. floor(hi / gs), exact floors */
+        cx0 = exact_floor_div(cl, gs), cx1 = lx >= 0 ? exact_floor_div(lx, gs) : -1;
+        cy0 = exact_floor_div(ct, gs), cy1 = ly >= 0 ? exact_floor_div(ly, gs) : -1;
+        bl = bt = 0; /* the float loops below run once; ids come from the integer ranges */
+        lx = ly = 0;
+    }
     for (double x = bl; x <= lx; x += gs)
-        for (double y = bt; y <= ly; y += gs) {
-            int id = (int)(x / gs) + (int)(y / gs) * g->cols;
+        for (double y = bt; y <= ly; y += gs)
+          for (int bx = canon ? cx0 : 0; bx <= (canon ? cx1 : 0); ++bx)
+            for (int by = canon ? cy0 : 0; by <= (canon ? cy1 : 0); ++by) {
+            int id = canon ? bx + by * g->cols : (int)(x / gs) + (int)(y / gs) * g->cols;
             if (id < 0 || id >= g->cols * g->cols) abort(); /* KeyError in the reference */
             if (g->stamp[id] == g->serial) continue;       /* ids is a set */
             g->stamp[id] = g->serial;
@@ -889,6 +909,7 @@ static void observe_agent(OracleEnv* e, int k, int agent, float* obs, double* ob
     static __thread GridTables g;
     memset(&g, 0, sizeof g);
     g.cols = cf->obs_mode == AGAR_OBS_CANONICAL ? G : (int)ceil(fov / gs); /* spatialHashTable.py:19 */
+    g.canonical = cf->obs_mode == AGAR_OBS_CANONICAL;
     Rect ra = rect_of(e, fx, fy, fov / 2);
     for (int s = 0; s < e->L.pellet_cap; ++s) { /* getPelletsInFov */
         uint32_t pk = e->pel[s];

@@ -153,6 +153,35 @@ def load_reference():
 
     ns.sht.spatialHashTable.__init__ = sht_init
 
+    # ... and bins with the mathematically exact floor((pos -+ radius) / gs) instead of int(x / gs) evaluated AT the
+    # bucket edges x = bucketLeft + k * gs (spatialHashTable.py:91-112), whose result hangs on the last bit of x / gs.
+    from fractions import Fraction
+    orig_ids_fp = ns.sht.spatialHashTable.getIdsForAreaFloatingPoint
+
+    def exact_floor_div(v, gs):
+        q = math.floor(v / gs)
+        fv, fg = Fraction(v), Fraction(gs)
+        while q * fg > fv:
+            q -= 1
+        while (q + 1) * fg <= fv:
+            q += 1
+        return q
+
+    def ids_fp(self, pos, radius):
+        if _current is None or _current.cfg.obs_mode != lay.OBS_CANONICAL:
+            return orig_ids_fp(self, pos, radius)
+        px, py = pos[0] - self.left, pos[1] - self.top
+        gs = self.bucketSize
+        ids = set()
+        x0, x1 = exact_floor_div(max(0, px - radius), gs), exact_floor_div(min(self.size - 1, px + radius), gs)
+        y0, y1 = exact_floor_div(max(0, py - radius), gs), exact_floor_div(min(self.size - 1, py + radius), gs)
+        for bx in range(x0, x1 + 1):
+            for by in range(y0, y1 + 1):
+                ids.add(bx + by * self.cols)
+        return ids
+
+    ns.sht.spatialHashTable.getIdsForAreaFloatingPoint = ids_fp
+
     # (iii) bookkeeping
     Cell, Field = ns.cell.Cell, ns.field.Field
     orig_cell_init = Cell.__init__

@@ -63,7 +63,10 @@ def test_portable_math_oracle_same_events_state_within_1e9(path):
     stats = {"n": 0, "bad": 0}
     replay(path, lambda cfg, seed, env_id: orc.OracleEnv(cfg, seed=seed, env_id=env_id, portable=True), rtol=1e-9,
            obs_rtol=1e-5, obs_stats=stats)
-    assert stats["n"] > 0 and stats["bad"] <= 0.03 * stats["n"], stats
+    if "canonical" in os.path.basename(path):  # AGAR_OBS_CANONICAL: exact floors -> no edge flips at all
+        assert stats["n"] > 0 and stats["bad"] == 0, stats
+    else:
+        assert stats["n"] > 0 and stats["bad"] <= 0.03 * stats["n"], stats
 
 
 def test_fixtures_exist():

@@ -22,7 +22,8 @@ def torch_cuda():
 
 @pytest.mark.parametrize("which,n_envs,frames,tile", [
     ("1", 64, 400, 32), ("1", 64, 200, 8), ("1", 70, 200, 4), ("1", 64, 200, 1), ("1", 33, 120, 2), ("1", 40, 120, 16),
-    ("3", 24, 400, 32), ("3", 24, 200, 8), ("r", 16, 240, 16), ("4", 6, 80, 32), ("4nv", 4, 60, 32), ("3", 12, 120, 4)])
+    ("3", 24, 400, 32), ("3", 24, 200, 8), ("r", 16, 240, 16), ("4", 6, 80, 32), ("4nv", 4, 60, 32), ("3", 12, 120, 4),
+    ("1c", 48, 240, 8), ("1c", 40, 160, 1), ("3c", 16, 240, 32), ("4c", 4, 48, 32)])
 def test_gpu_equals_oracle_bit_for_bit(torch_cuda, which, n_envs, frames, tile):
     """Every field of every env record, every event, every observation / reward / done, each frame."""
     import gpu_check
@@ -191,7 +192,10 @@ def test_gpu_against_reference_golden(torch_cuda, path):
             d = lay.compare_records(lay.Record(L, z["records"][rec_at[t]].copy()), b.dump(0), rtol=1e-9,
                                     what="frame %d " % t, check_hist=False)
             assert not d, d
-    assert n_el > 0 and n_bad <= 0.03 * n_el, (n_bad, n_el)  # bucket-edge flips only
+    if "canonical" in os.path.basename(path):
+        assert n_el > 0 and n_bad == 0, (n_bad, n_el)  # robust binning: observations agree with the reference's
+    else:
+        assert n_el > 0 and n_bad <= 0.03 * n_el, (n_bad, n_el)  # bucket-edge flips only
 
 
 def test_dqn_consumer_zero_copy(torch_cuda):

@@ -10,7 +10,10 @@ from oracle import oracle as orc
 KWS = {"1": dict(), "3": dict(num_nn=1, num_greedy=1, virus=True, split=True, eject=True),
        "4": dict(num_nn=8, num_greedy=8, virus=True, split=True, eject=True),
        "r": dict(num_nn=1, num_greedy=1, num_random=1, virus=True, split=True, eject=True),
-       "4nv": dict(num_nn=8, num_greedy=8, virus=False, split=True, eject=True)}
+       "4nv": dict(num_nn=8, num_greedy=8, virus=False, split=True, eject=True),
+       # AGAR_OBS_CANONICAL: robust observation binning (exact floors, always G columns)
+       "1c": dict(obs_mode=1), "3c": dict(num_nn=1, num_greedy=1, virus=True, split=True, eject=True, obs_mode=1),
+       "4c": dict(num_nn=8, num_greedy=8, virus=True, split=True, eject=True, obs_mode=1)}
 
 
 def records(batch):
