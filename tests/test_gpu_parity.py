@@ -30,6 +30,26 @@ def test_gpu_equals_oracle_bit_for_bit(torch_cuda, which, n_envs, frames, tile):
     assert gpu_check.check(which, n_envs=n_envs, frames=frames, tile_width=tile, verbose=False)
 
 
+VARIATIONS = [
+    (dict(mass_as_reward=True), 8), (dict(frame_skip=3, reward_scale=1.0, reward_term=0.5), 4), (dict(grid=7), 8),
+    (dict(grid=13, num_nn=1, num_greedy=1), 32), (dict(num_nn=2, num_random=1, split=True), 32),
+    (dict(num_nn=1, num_greedy=2, virus=True), 16),
+    (dict(num_nn=1, num_greedy=1, virus=True, split=True, eject=True, death_term=-10.0, death_factor=0.5), 32),
+    (dict(num_nn=3, num_greedy=1, split=True, eject=True, obs_mode=1), 8),
+    (dict(overrides={"use_second_last_action": 1, "self_grid_slf": 1, "enemy_grid_slf": 1}, num_nn=1, num_greedy=1,
+          virus=True, split=True, eject=True), 32),
+    (dict(overrides={"use_totalmass": 0}), 8), (dict(overrides={"use_fovsize": 0}), 2), (dict(pellet_spawn=False), 8),
+]
+
+
+@pytest.mark.parametrize("kw,tile", VARIATIONS, ids=[str(i) for i in range(len(VARIATIONS))])
+def test_config_variations(torch_cuda, kw, tile):
+    """Flags the default configs do not exercise (reward variants, frame-skip, grid sizes, channel subsets, bot
+    mixes, missing extras): CUDA == oracle, every field, every frame."""
+    import gpu_check
+    assert gpu_check.check(kw, n_envs=10, frames=120, tile_width=tile, verbose=False)
+
+
 def _batch(cfg, n, **kw):
     from aigar_b200.env import AgarBatch
     return AgarBatch(cfg, n, **kw)

@@ -41,3 +41,26 @@ def test_reset_matches_reference():
         ora.frame(a)
     d = lay.compare_records(ref.to_record(tr), ora.record, what="after reset+60 ")
     assert not d, d
+
+
+VARIATIONS = [
+    dict(mass_as_reward=True),
+    dict(frame_skip=3, reward_scale=1.0, reward_term=0.5),
+    dict(grid=7),
+    dict(grid=13, num_nn=1, num_greedy=1),
+    dict(num_nn=2, num_random=1, split=True),                      # two agents, a random bot, split without eject
+    dict(num_nn=1, num_greedy=2, virus=True),                      # viruses without split: explosions only
+    dict(num_nn=1, num_greedy=1, virus=True, split=True, eject=True, death_term=-10.0, death_factor=0.5),
+    dict(num_nn=3, num_greedy=1, split=True, eject=True, obs_mode=1),
+    dict(overrides={"use_second_last_action": 1, "self_grid_slf": 1, "enemy_grid_slf": 1}, num_nn=1, num_greedy=1,
+         virus=True, split=True, eject=True),
+]
+
+
+@pytest.mark.parametrize("kw", VARIATIONS, ids=[str(i) for i in range(len(VARIATIONS))])
+def test_config_variations_equal_reference(kw):
+    """Flags of networkParameters.py the default configs do not exercise: reward variants, frame-skip, grid sizes,
+    channel subsets, bot mixes."""
+    import compare_oracle_ref as cmp
+    frames = 160 if kw.get("num_nn", 1) + kw.get("num_greedy", 0) + kw.get("num_random", 0) <= 2 else 90
+    assert cmp.run(kw, frames, seed=31, verbose=False)

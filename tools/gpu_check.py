@@ -22,7 +22,7 @@ def records(batch):
 
 
 def check(which="1", n_envs=32, frames=200, seed=3, first_env=5, tile_width=None, every=1, event_cap=64, verbose=True):
-    cfg = lay.derive_config(event_cap=event_cap, **KWS[which])
+    cfg = lay.derive_config(event_cap=event_cap, **(which if isinstance(which, dict) else KWS[which]))
     batch = AgarBatch(cfg, n_envs, seed=seed, first_env_id=first_env, tile_width=tile_width)
     L = batch.layout
     oras = [orc.OracleEnv(cfg, seed=seed, env_id=first_env + i, portable=True) for i in range(n_envs)]
@@ -71,7 +71,7 @@ def check(which="1", n_envs=32, frames=200, seed=3, first_env=5, tile_width=None
     if not cmp("final"):
         print("\n".join(bad[:30])); return False
     if verbose:
-        print("OK config %s: %d envs x %d frames bit-exact (W=%d)" % (which, n_envs, frames, batch.tile_width))
+        print("OK config %s: %d envs x %d frames bit-exact (W=%d)" % (which if not isinstance(which, dict) else "custom", n_envs, frames, batch.tile_width))
     return True
 
 
