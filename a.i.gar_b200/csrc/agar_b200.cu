@@ -39,12 +39,23 @@ __device__ __forceinline__ void stage_out(const DevParams& P, uint8_t* state, in
         dst[i] = ((const uint2*)(g_smem + (size_t)e * P.rec_stride))[w];
     }
 }
+__device__ __forceinline__ int pel_cache_bytes(const DevParams& P) { return (P.L.pellet_cap * 4 + 15) / 16 * 16; }
+/* stage == 2: copy the pellet pools of this CTA's envs between HBM and their shared-memory cache */
+__device__ __forceinline__ void pel_cache_copy(const DevParams& P, uint8_t* state, int env0, int n_here, int tiles, bool in) {
+    const int words = P.L.pellet_cap;
+    for (int i = threadIdx.x; i < n_here * words; i += blockDim.x) {
+        int e = i / words, w = i - e * words;
+        uint32_t* g = (uint32_t*)(state + (size_t)(env0 + e) * P.L.record_bytes + P.L.off_pellets) + w;
+        uint32_t* s = (uint32_t*)(g_smem + (size_t)tiles * P.scratch_bytes + (size_t)e * pel_cache_bytes(P)) + w;
+        if (in) *s = *g; else *g = *s;
+    }
+    __syncthreads();
+}
 template <int W>
 __device__ __forceinline__ void bind_ctx(Ctx<W>& c, const DevParams& P, int tile_id, int tiles, int env, uint8_t* state) {
     c.lane = c.t.thread_rank();
     c.env_id = (uint32_t)(P.first_env + (uint64_t)env);
-    c.rec = P.stage ? g_smem + (size_t)tile_id * P.rec_stride : nullptr;
-    if (!P.stage) c.rec = state + (size_t)env * P.L.record_bytes; /* big records: step in place, through L1 / L2 */
+    c.rec = P.stage == 1 ? g_smem + (size_t)tile_id * P.rec_stride : state + (size_t)env * P.L.record_bytes;
     c.h = (AgarEnvHeader*)(c.rec + P.L.off_header);
     c.pl = (AgarPlayer*)(c.rec + P.L.off_players);
     c.cells = (AgarCell*)(c.rec + P.L.off_cells);
@@ -54,7 +65,9 @@ __device__ __forceinline__ void bind_ctx(Ctx<W>& c, const DevParams& P, int tile
     c.pel = (uint32_t*)(c.rec + P.L.off_pellets);
     c.hist = (float*)(c.rec + P.L.off_hist);
     c.ev = (AgarEvent*)(c.rec + P.L.off_events);
-    c.scratch = g_smem + (P.stage ? (size_t)tiles * P.rec_stride : 0) + (size_t)tile_id * P.scratch_bytes;
+    c.scratch = g_smem + (P.stage == 1 ? (size_t)tiles * P.rec_stride : 0) + (size_t)tile_id * P.scratch_bytes;
+    if (P.stage == 2) /* big records stay in HBM / L2; only the pellet pool — what every scan reads — is cached on chip */
+        c.pel = (uint32_t*)(g_smem + (size_t)tiles * P.scratch_bytes + (size_t)tile_id * pel_cache_bytes(P));
 }
 
 /* ------------------------------------------------------------------ the step kernel */
@@ -65,7 +78,8 @@ k_main(const __grid_constant__ DevParams P, uint8_t* __restrict__ state, const f
     const int tiles = blockDim.x / W;
     const int env0 = blockIdx.x * tiles;
     const int n_here = min(tiles, P.n_envs - env0);
-    if (P.stage) stage_in(P, state, env0, n_here, false);
+    if (P.stage == 1) stage_in(P, state, env0, n_here, false);
+    if (P.stage == 2) pel_cache_copy(P, state, env0, n_here, tiles, true);
     const int tile_id = threadIdx.x / W;
     if (tile_id < n_here) {
         Ctx<W> c(cg::tiled_partition<W>(cg::this_thread_block()));
@@ -109,7 +123,11 @@ k_main(const __grid_constant__ DevParams P, uint8_t* __restrict__ state, const f
         if (flags & KF_OBS_AFTER)
             for (int a = 0; a < A; ++a) nn_turn_begin<W, FULL>(c, P, a, obs_env ? obs_env + (size_t)a * SL : nullptr);
     }
-    if (P.stage) stage_out(P, state, env0, n_here);
+    if (P.stage == 1) stage_out(P, state, env0, n_here);
+    if (P.stage == 2) {
+        __syncthreads();
+        pel_cache_copy(P, state, env0, n_here, tiles, false);
+    }
 }
 
 
@@ -198,7 +216,7 @@ k_init(const __grid_constant__ DevParams P, uint8_t* __restrict__ state, const u
     const int tiles = blockDim.x / W;
     const int env0 = blockIdx.x * tiles;
     const int n_here = min(tiles, P.n_envs - env0);
-    if (P.stage)
+    if (P.stage == 1)
         stage_in(P, state, env0, n_here, mode == 0);
     else if (mode == 0) { /* records stay in HBM: clear them in place */
         const int chunks = (int)(P.L.record_bytes / 8);
@@ -206,6 +224,7 @@ k_init(const __grid_constant__ DevParams P, uint8_t* __restrict__ state, const u
         for (int i = threadIdx.x; i < n_here * chunks; i += blockDim.x) dst[i] = make_uint2(0u, 0u);
         __syncthreads();
     }
+    if (P.stage == 2) pel_cache_copy(P, state, env0, n_here, tiles, true);
     const int tile_id = threadIdx.x / W;
     if (tile_id < n_here && (mask == nullptr || mode == 0 || mask[env0 + tile_id])) {
         Ctx<W> c(cg::tiled_partition<W>(cg::this_thread_block()));
@@ -257,7 +276,11 @@ k_init(const __grid_constant__ DevParams P, uint8_t* __restrict__ state, const u
             c.t.sync();
         }
     }
-    if (P.stage) stage_out(P, state, env0, n_here);
+    if (P.stage == 1) stage_out(P, state, env0, n_here);
+    if (P.stage == 2) {
+        __syncthreads();
+        pel_cache_copy(P, state, env0, n_here, tiles, false);
+    }
 }
 
 /* agar_get: one thread per (env, agent) or per env, straight from HBM */
@@ -343,7 +366,8 @@ static bool config_is_simple(const AgarConfig& c, const AgarLayout& L) {
 /* pick the launch shape for tile width W; returns false if one record does not fit in shared memory */
 static bool plan_launch(AgarEnv* e, int W) {
     const size_t budget = 200 * 1024;
-    size_t per_tile = (e->P.stage ? (size_t)e->P.rec_stride : 0) + (size_t)e->P.scratch_bytes;
+    size_t per_tile = (e->P.stage == 1 ? (size_t)e->P.rec_stride : 0) + (size_t)e->P.scratch_bytes +
+                      (e->P.stage == 2 ? (size_t)((e->L.pellet_cap * 4 + 15) / 16 * 16) : 0);
     int tiles = 128 / W;
     while (tiles > 1 && per_tile * tiles > budget) tiles >>= 1;
     if (per_tile * tiles > budget) return false;
@@ -477,8 +501,8 @@ extern "C" int agar_create(const AgarConfig* cfg, int n_envs, int device, uint64
     P.full = e->full;
     /* small records are stepped in shared memory; big ones (multi-agent arenas: 60 KB) in place through L1 / L2,
      * which keeps >= 32 warps per SM resident instead of 3 (profiles/r01_sweep_full.txt) */
-    P.stage = L.record_bytes <= 16 * 1024;
-    if (getenv("AGAR_STAGE")) P.stage = atoi(getenv("AGAR_STAGE")) != 0;
+    P.stage = L.record_bytes <= 16 * 1024 ? 1 : 2; /* 2: only the pellet pool is cached in shared memory */
+    if (getenv("AGAR_STAGE")) P.stage = atoi(getenv("AGAR_STAGE"));
     int vel_bytes = e->full ? L.n_players * L.cell_cap * 2 * 8 : 0;
     int obs_bytes = obs_scratch_bytes(L.grid_squares, e->full != 0);
     P.scratch_bytes = ((vel_bytes > obs_bytes ? vel_bytes : obs_bytes) + 15) / 16 * 16 + 8;

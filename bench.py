@@ -326,6 +326,40 @@ def main():
             b3.close()
         except Exception as ex:
             extra["dqn_65536"] = {"error": str(ex)[:200]}
+        try:  # transitions from the env's buffers into the GPU replay ring, prioritized sampling
+            from aigar_b200.replay import GpuReplayBuffer
+            E4 = 65536
+            b4 = AgarBatch(cfg, E4, device=local, seed=7, first_env_id=3 * 10 ** 6)
+            rp = GpuReplayBuffer(1 << 20, L.state_len, 4, prioritized=True)
+            o0 = b4.observe().clone()
+            a4 = torch.rand((E4, 1, 4), device=batch.device)
+            o1 = b4.step_observe(a4, PERIOD)
+            v4, d4, r4 = b4.get(lay.GET_VALID), b4.get(lay.GET_DONE), b4.get(lay.GET_REWARD)
+            for _ in range(3):
+                rp.add_batch(o0, a4, r4, o1, d4, v4)
+            u = torch.rand(4096, dtype=torch.float64, device=batch.device)
+            rp.sample(u)
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(10):
+                rp.add_batch(o0, a4, r4, o1, d4, v4)
+            e.record()
+            torch.cuda.synchronize()
+            add_ms = s.elapsed_time(e) / 10
+            s.record()
+            for _ in range(10):
+                rp.sample(u)
+            e.record()
+            torch.cuda.synchronize()
+            smp_ms = s.elapsed_time(e) / 10
+            bytes_tr = (2 * L.state_len + 4 + 1) * 4 + 1
+            extra["replay"] = {"add_transitions_per_s": E4 / (add_ms * 1e-3), "add_gbs": 2 * E4 * bytes_tr / (add_ms * 1e-3) / 1e9,
+                               "per_sample_4096_ms": smp_ms, "capacity": 1 << 20, "prioritized": True,
+                               "note": "add = block scan + one warp per transition + 20 tree levels; GB/s counts read + write"}
+            b4.close(), rp.close()
+        except Exception as ex:
+            extra["replay"] = {"error": str(ex)[:200]}
 
     if dist is not None:
         dist.barrier()

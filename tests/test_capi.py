@@ -11,9 +11,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def declared_functions():
-    src = open(os.path.join(ROOT, "include", "agar_b200.h")).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(agar_[a-z_]+)\s*\(", src)))
+    names = set()
+    for header in ("agar_b200.h", "agar_replay.h"):
+        src = open(os.path.join(ROOT, "include", header)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names |= set(re.findall(r"\b(agar_[a-z_]+)\s*\(", src))
+    return sorted(names)
 
 
 def test_header_declares_the_surface():
