@@ -87,41 +87,45 @@ k_main(const __grid_constant__ DevParams P, uint8_t* __restrict__ state, const f
         bind_ctx(c, P, tile_id, tiles, env, state);
         const int A = P.L.n_agents, K = P.L.n_players, SL = P.L.state_len;
         float* obs_env = obs ? obs + (size_t)env * A * SL : nullptr;
-        for (int d = 0; d < n_dec; ++d) {
-            if (flags & KF_OBS_BEFORE)
-                for (int a = 0; a < A; ++a) nn_turn_begin<W, FULL>(c, P, a, obs_env ? obs_env + (size_t)a * SL : nullptr);
-            for (int f = 0; f < n_frames; ++f) {
-                if (c.lane == 0) c.h->n_events = 0;
-                for (int k = 0; k < K; ++k) {
-                    if (!FULL || P.cfg.bot_type[k] == AGAR_BOT_NN) {
-                        nn_turn_begin<W, FULL>(c, P, k, nullptr);
-                        if (c.lane == 0) {
-                            float act[4] = {0.f, 0.f, 0.f, 0.f};
-                            if (c.pl[k].bot.need_action) {
-                                if (flags & KF_RANDOM_ACTIONS) { /* random-action driver */
-                                    uint32_t w[4];
-                                    philox(dec_base + (uint32_t)d, 7u, c.env_id, (uint32_t)k, (uint32_t)P.seed,
-                                           (uint32_t)(P.seed >> 32), w);
-                                    for (int i = 0; i < 4; ++i) act[i] = (float)(w[i] >> 8) * (1.0f / 16777216.0f);
-                                } else {
-                                    const float* ap = actions + ((size_t)env * A + k) * 4;
-                                    for (int i = 0; i < 4; ++i) act[i] = ap[i];
-                                }
+        /* One loop with ONE call site per helper: the multi-agent frame is ~25 k SASS instructions and instruction
+         * fetch is its top stall (profiles/r01_k_main_cfg3_*), so nothing big may be inlined twice.  Iteration `it` is
+         * frame f of decision d; the trailing observation (KF_OBS_AFTER) is one extra iteration without a frame. */
+        const int total = n_dec * n_frames;
+        for (int it = 0; it <= total; ++it) {
+            const bool last = it == total;
+            if (last && !(flags & KF_OBS_AFTER)) break;
+            const int f = n_frames > 0 ? it % n_frames : 0, d = n_frames > 0 ? it / n_frames : 0;
+            const bool emit = last || (f == 0 && (flags & KF_OBS_BEFORE)); /* observations leave the kernel here */
+            if (!last && c.lane == 0) c.h->n_events = 0;
+            for (int k = 0; k < K; ++k) {
+                if (!FULL || P.cfg.bot_type[k] == AGAR_BOT_NN) {
+                    nn_turn_begin<W, FULL>(c, P, k, (emit && obs_env) ? obs_env + (size_t)k * SL : nullptr);
+                    if (last) continue;
+                    if (c.lane == 0) {
+                        float act[4] = {0.f, 0.f, 0.f, 0.f};
+                        if (c.pl[k].bot.need_action) {
+                            if (flags & KF_RANDOM_ACTIONS) { /* random-action driver */
+                                uint32_t w[4];
+                                philox(dec_base + (uint32_t)d, 7u, c.env_id, (uint32_t)k, (uint32_t)P.seed,
+                                       (uint32_t)(P.seed >> 32), w);
+                                for (int i = 0; i < 4; ++i) act[i] = (float)(w[i] >> 8) * (1.0f / 16777216.0f);
+                            } else {
+                                const float* ap = actions + ((size_t)env * A + k) * 4;
+                                for (int i = 0; i < 4; ++i) act[i] = ap[i];
                             }
-                            nn_turn_end(c, P, k, act);
                         }
-                        c.t.sync();
-                    } else if (FULL) {
-                        scripted_turn(c, P, k);
+                        nn_turn_end(c, P, k, act);
                     }
+                    c.t.sync();
+                } else if (FULL && !last) {
+                    scripted_turn(c, P, k);
                 }
-                field_update<W, FULL>(c, P);
-                if (c.lane == 0) c.h->frame += 1;
-                c.t.sync();
             }
+            if (last) break;
+            field_update<W, FULL>(c, P);
+            if (c.lane == 0) c.h->frame += 1;
+            c.t.sync();
         }
-        if (flags & KF_OBS_AFTER)
-            for (int a = 0; a < A; ++a) nn_turn_begin<W, FULL>(c, P, a, obs_env ? obs_env + (size_t)a * SL : nullptr);
     }
     if (P.stage == 1) stage_out(P, state, env0, n_here);
     if (P.stage == 2) {
