@@ -72,7 +72,7 @@ __device__ __forceinline__ void bind_ctx(Ctx<W>& c, const DevParams& P, int tile
 
 /* ------------------------------------------------------------------ the step kernel */
 template <int W, bool FULL>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(512)
 k_main(const __grid_constant__ DevParams P, uint8_t* __restrict__ state, const float* __restrict__ actions,
        float* __restrict__ obs, int n_frames, int n_dec, int flags, uint32_t dec_base) {
     const int tiles = blockDim.x / W;
@@ -81,50 +81,65 @@ k_main(const __grid_constant__ DevParams P, uint8_t* __restrict__ state, const f
     if (P.stage == 1) stage_in(P, state, env0, n_here, false);
     if (P.stage == 2) pel_cache_copy(P, state, env0, n_here, tiles, true);
     const int tile_id = threadIdx.x / W;
-    if (tile_id < n_here) {
+    const bool active = tile_id < n_here;
+    {
         Ctx<W> c(cg::tiled_partition<W>(cg::this_thread_block()));
-        const int env = env0 + tile_id;
-        bind_ctx(c, P, tile_id, tiles, env, state);
+        const int env = env0 + (active ? tile_id : 0);
+        bind_ctx(c, P, active ? tile_id : 0, tiles, env, state);
         const int A = P.L.n_agents, K = P.L.n_players, SL = P.L.state_len;
         float* obs_env = obs ? obs + (size_t)env * A * SL : nullptr;
-        /* One loop with ONE call site per helper: the multi-agent frame is ~25 k SASS instructions and instruction
+        const bool psync = P.phase_sync != 0;             /* barriers at frame start and before the field update */
+        const bool psync_field = P.phase_sync == 2 || P.phase_sync >= 4; /* ... between the field phases */
+        const bool psync_bots = P.phase_sync >= 3;        /* ... between bot turns */
+        /* One loop with ONE call site per helper: the multi-agent frame is ~22 k SASS instructions and instruction
          * fetch is its top stall (profiles/r01_k_main_cfg3_*), so nothing big may be inlined twice.  Iteration `it` is
-         * frame f of decision d; the trailing observation (KF_OBS_AFTER) is one extra iteration without a frame. */
+         * frame f of decision d; the trailing observation (KF_OBS_AFTER) is one extra iteration without a frame.
+         * With phase_sync, CTA barriers between the phases keep all warps of the CTA in the same code region, so the
+         * instruction cache serves them together (idle tiles of a partly filled CTA only hit the barriers). */
         const int total = n_dec * n_frames;
         for (int it = 0; it <= total; ++it) {
             const bool last = it == total;
             if (last && !(flags & KF_OBS_AFTER)) break;
+            if (psync) __syncthreads();
             const int f = n_frames > 0 ? it % n_frames : 0, d = n_frames > 0 ? it / n_frames : 0;
             const bool emit = last || (f == 0 && (flags & KF_OBS_BEFORE)); /* observations leave the kernel here */
-            if (!last && c.lane == 0) c.h->n_events = 0;
+            if (active && !last && c.lane == 0) c.h->n_events = 0;
             for (int k = 0; k < K; ++k) {
-                if (!FULL || P.cfg.bot_type[k] == AGAR_BOT_NN) {
-                    nn_turn_begin<W, FULL>(c, P, k, (emit && obs_env) ? obs_env + (size_t)k * SL : nullptr);
-                    if (last) continue;
-                    if (c.lane == 0) {
-                        float act[4] = {0.f, 0.f, 0.f, 0.f};
-                        if (c.pl[k].bot.need_action) {
-                            if (flags & KF_RANDOM_ACTIONS) { /* random-action driver */
-                                uint32_t w[4];
-                                philox(dec_base + (uint32_t)d, 7u, c.env_id, (uint32_t)k, (uint32_t)P.seed,
-                                       (uint32_t)(P.seed >> 32), w);
-                                for (int i = 0; i < 4; ++i) act[i] = (float)(w[i] >> 8) * (1.0f / 16777216.0f);
-                            } else {
-                                const float* ap = actions + ((size_t)env * A + k) * 4;
-                                for (int i = 0; i < 4; ++i) act[i] = ap[i];
+                if (psync_bots && k > 0) __syncthreads(); /* one bot turn per barrier interval */
+                if (active) {
+                    if (!FULL || P.cfg.bot_type[k] == AGAR_BOT_NN) {
+                        nn_turn_begin<W, FULL>(c, P, k, (emit && obs_env) ? obs_env + (size_t)k * SL : nullptr);
+                        if (last) continue;
+                        if (c.lane == 0) {
+                            float act[4] = {0.f, 0.f, 0.f, 0.f};
+                            if (c.pl[k].bot.need_action) {
+                                if (flags & KF_RANDOM_ACTIONS) { /* random-action driver */
+                                    uint32_t w[4];
+                                    philox(dec_base + (uint32_t)d, 7u, c.env_id, (uint32_t)k, (uint32_t)P.seed,
+                                           (uint32_t)(P.seed >> 32), w);
+                                    for (int i = 0; i < 4; ++i) act[i] = (float)(w[i] >> 8) * (1.0f / 16777216.0f);
+                                } else {
+                                    const float* ap = actions + ((size_t)env * A + k) * 4;
+                                    for (int i = 0; i < 4; ++i) act[i] = ap[i];
+                                }
                             }
+                            nn_turn_end(c, P, k, act);
                         }
-                        nn_turn_end(c, P, k, act);
+                        c.t.sync();
+                    } else if (FULL && !last) {
+                        scripted_turn(c, P, k);
                     }
-                    c.t.sync();
-                } else if (FULL && !last) {
-                    scripted_turn(c, P, k);
                 }
             }
             if (last) break;
-            field_update<W, FULL>(c, P);
-            if (c.lane == 0) c.h->frame += 1;
-            c.t.sync();
+            for (int ph = 0; ph < AGAR_FIELD_PHASES; ++ph) {
+                if (ph == 0 ? psync : psync_field) __syncthreads();
+                if (active) field_update_phase<W, FULL>(c, P, ph);
+            }
+            if (active) {
+                if (c.lane == 0) c.h->frame += 1;
+                c.t.sync();
+            }
         }
     }
     if (P.stage == 1) stage_out(P, state, env0, n_here);
@@ -215,7 +230,7 @@ k_simple(const __grid_constant__ DevParams P, const SimplePlan SP, uint8_t* __re
 /* mode 0: Model(...) + createBot*K + Model.initialize (model.py:51,154-162,90-94; field.py:57-67)
  * mode 1: Model.resetModel -> Field.reset (field.py:69-83)      mode 2: Model.resetBots (bot.py:125-164) */
 template <int W, bool FULL>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(512)
 k_init(const __grid_constant__ DevParams P, uint8_t* __restrict__ state, const uint8_t* __restrict__ mask, int mode) {
     const int tiles = blockDim.x / W;
     const int env0 = blockIdx.x * tiles;
@@ -372,8 +387,11 @@ static bool plan_launch(AgarEnv* e, int W) {
     const size_t budget = 200 * 1024;
     size_t per_tile = (e->P.stage == 1 ? (size_t)e->P.rec_stride : 0) + (size_t)e->P.scratch_bytes +
                       (e->P.stage == 2 ? (size_t)((e->L.pellet_cap * 4 + 15) / 16 * 16) : 0);
-    int tiles = 128 / W;
-    while (tiles > 1 && per_tile * tiles > budget) tiles >>= 1;
+    int tiles = e->full ? 512 / W : 128 / W; /* as many envs per CTA as fit: the barriers then align more warps */
+    if (getenv("AGAR_MAX_TILES")) tiles = atoi(getenv("AGAR_MAX_TILES"));
+    if (tiles * W > 512) tiles = 512 / W;
+    while (tiles > 1 && per_tile * tiles > budget) tiles -= 1;
+    if (W == 32 && tiles > 4) tiles -= tiles % 4; /* warps spread evenly over the four schedulers of an SM */
     if (per_tile * tiles > budget) return false;
     e->W = W;
     e->tiles = tiles;
@@ -507,6 +525,8 @@ extern "C" int agar_create(const AgarConfig* cfg, int n_envs, int device, uint64
      * which keeps >= 32 warps per SM resident instead of 3 (profiles/r01_sweep_full.txt) */
     P.stage = L.record_bytes <= 16 * 1024 ? 1 : 2; /* 2: only the pellet pool is cached in shared memory */
     if (getenv("AGAR_STAGE")) P.stage = atoi(getenv("AGAR_STAGE"));
+    /* multi-agent kernels are instruction-fetch bound: lock-step the CTA's warps phase by phase (measured 2x) */
+    P.phase_sync = getenv("AGAR_PHASE_SYNC") ? atoi(getenv("AGAR_PHASE_SYNC")) : e->full;
     int vel_bytes = e->full ? L.n_players * L.cell_cap * 2 * 8 : 0;
     int obs_bytes = obs_scratch_bytes(L.grid_squares, e->full != 0);
     P.scratch_bytes = ((vel_bytes > obs_bytes ? vel_bytes : obs_bytes) + 15) / 16 * 16 + 8;

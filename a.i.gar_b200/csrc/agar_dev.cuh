@@ -38,7 +38,7 @@ struct DevParams {
     AgarConfig cfg;
     AgarLayout L;
     int S, nb, n_envs, rec_stride; /* rec_stride: bytes between staged records in shared memory */
-    int scratch_bytes, full, stage, pad1; /* stage: 1 = records live in shared memory during a launch, 0 = in HBM/L2 */
+    int scratch_bytes, full, stage, phase_sync; /* phase_sync: CTA barriers between frame phases keep the warps' instruction streams aligned */ /* stage: 1 = records live in shared memory during a launch, 0 = in HBM/L2 */
     double move_speed, decay_rate, blob_mass, virus_split_mass, start_radius, virus_radius;
     double pellet_r[4];
     double pow_n[17];
@@ -1025,44 +1025,54 @@ DEV bool any_virus_blob_hit(Ctx<W>& c, const DevParams& P) {
 
 /* cooperative; field.py:85-92 */
 template <int W, bool FULL>
-DEV void field_update(Ctx<W>& c, const DevParams& P) {
-    if (FULL) update_viruses_blobs(c, P);
-    update_players<W, FULL>(c, P);
-    if (FULL) {
-        /* mergePlayerCells: only players with >= 2 cells can merge */
-        for (int k = 0; k < P.L.n_players; ++k) {
-            /* any() is also the barrier that keeps lane 0's writes away from the other lanes' reads of n_cells */
-            if (c.t.any(c.pl[k].alive && c.pl[k].n_cells > 1)) {
-                if (c.lane == 0) merge_player_cells_seq(c, P, k);
+DEV void field_update_phase(Ctx<W>& c, const DevParams& P, int phase) {
+    /* the frame in AGAR_FIELD_PHASES pieces, so that the caller can put CTA barriers between them (the warps of a CTA
+     * then fetch the same instructions together; see k_main) */
+    if (phase == 0) {
+        if (FULL) update_viruses_blobs(c, P);
+        update_players<W, FULL>(c, P);
+    } else if (phase == 1) {
+        if (FULL) {
+            /* mergePlayerCells: only players with >= 2 cells can merge */
+            for (int k = 0; k < P.L.n_players; ++k) {
+                /* any() is also the barrier that keeps lane 0's writes away from the other lanes' reads of n_cells */
+                if (c.t.any(c.pl[k].alive && c.pl[k].n_cells > 1)) {
+                    if (c.lane == 0) merge_player_cells_seq(c, P, k);
+                    c.t.sync();
+                }
+            }
+            if (c.h->n_viruses && c.h->n_blobs && any_virus_blob_hit(c, P)) {
+                if (c.lane == 0) virus_blob_overlap_seq(c, P);
+                c.t.sync();
+            }
+            if (any_player_mote_hit(c, P, c.vir, c.h->n_viruses, true)) {
+                if (c.lane == 0) player_virus_overlap_seq(c, P);
                 c.t.sync();
             }
         }
-        if (c.h->n_viruses && c.h->n_blobs && any_virus_blob_hit(c, P)) {
-            if (c.lane == 0) virus_blob_overlap_seq(c, P);
-            c.t.sync();
+    } else if (phase == 2) {
+        /* playerPelletOverlap */
+        if (!FULL) {
+            cell_eats_pellets(c, P, 0, 0, false);
+        } else {
+            bool fat_too = P.L.fat_cap > 0;
+            for (int k = 0; k < P.L.n_players; ++k) {
+                if (!c.pl[k].alive) continue;
+                for (int ci = 0; ci < c.pl[k].n_cells; ++ci) cell_eats_pellets(c, P, k, ci, fat_too && c.h->n_fat > 0);
+            }
         }
-        if (any_player_mote_hit(c, P, c.vir, c.h->n_viruses, true)) {
-            if (c.lane == 0) player_virus_overlap_seq(c, P);
-            c.t.sync();
-        }
-    }
-    /* playerPelletOverlap */
-    if (!FULL) {
-        cell_eats_pellets(c, P, 0, 0, false);
     } else {
-        bool fat_too = P.L.fat_cap > 0;
-        for (int k = 0; k < P.L.n_players; ++k) {
-            if (!c.pl[k].alive) continue;
-            for (int ci = 0; ci < c.pl[k].n_cells; ++ci) cell_eats_pellets(c, P, k, ci, fat_too && c.h->n_fat > 0);
+        if (FULL) {
+            if (any_player_mote_hit(c, P, c.blob, c.h->n_blobs, false)) {
+                if (c.lane == 0) player_blob_overlap_seq(c, P);
+                c.t.sync();
+            }
+            if (P.L.n_players > 1 && any_player_player_hit(c, P)) {
+                if (c.lane == 0) player_player_overlap_seq(c, P);
+                c.t.sync();
+            }
         }
-        if (any_player_mote_hit(c, P, c.blob, c.h->n_blobs, false)) {
-            if (c.lane == 0) player_blob_overlap_seq(c, P);
-            c.t.sync();
-        }
-        if (P.L.n_players > 1 && any_player_player_hit(c, P)) {
-            if (c.lane == 0) player_player_overlap_seq(c, P);
-            c.t.sync();
-        }
+        spawn_stuff<W, FULL>(c, P);
     }
-    spawn_stuff<W, FULL>(c, P);
 }
+#define AGAR_FIELD_PHASES 4
