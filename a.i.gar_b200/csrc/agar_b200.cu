@@ -152,12 +152,13 @@ k_main(const __grid_constant__ DevParams P, uint8_t* __restrict__ state, const f
 
 /* ------------------------------------------------------------------ register-resident kernel (agar_simple.cuh) */
 struct SimplePlan {
+    int frame_sync; /* CTA barrier at every frame: the warps of a CTA fetch the same instructions together */
     int strideB; /* bytes between the staged [pellets .. end of record] regions of consecutive envs */
 };
 /* one lane per env is throughput-bound: cap registers at 128 for 8 CTAs / SM (measured +10..50 % at >= 64k envs);
  * wider tiles are latency-bound at small env counts and prefer the uncapped allocation (measured) */
 template <int W>
-__global__ void __launch_bounds__(64, W == 1 ? 8 : 1)
+__global__ void __launch_bounds__(256, W == 1 ? 2 : 1)
 k_simple(const __grid_constant__ DevParams P, const SimplePlan SP, uint8_t* __restrict__ state, const float* __restrict__ actions,
          float* __restrict__ obs, int n_frames, int n_dec, int flags, uint32_t dec_base) {
     const int per = blockDim.x / W; /* envs per CTA */
@@ -196,6 +197,8 @@ k_simple(const __grid_constant__ DevParams P, const SimplePlan SP, uint8_t* __re
             s_observe<W>(r, q, P, d_o != 0, row, sub);
         }
         for (int f = 0; f < n_frames; ++f) {
+            if (SP.frame_sync == 1 || SP.frame_sync == 4) __syncthreads();
+            if (SP.frame_sync == 2) __syncwarp();
             r.n_events = 0;
             int d_o = s_turn_begin(r, P);
             s_observe<W>(r, q, P, d_o != 0, nullptr, sub);
@@ -211,6 +214,7 @@ k_simple(const __grid_constant__ DevParams P, const SimplePlan SP, uint8_t* __re
                 }
             }
             s_turn_end(r, P, act);
+            if (SP.frame_sync == 4) __syncthreads();
             s_field_update<W>(r, q, P, env_id, sub);
         }
     }
@@ -473,10 +477,13 @@ extern "C" int agar_set_tile_width(AgarEnv* e, int W) {
         int tail_words = (int)((e->L.record_bytes - e->L.off_pellets) / 4);
         e->sp.strideB = (tail_words | 1) * 4;
         if (e->L.pellet_cap > 128 * W) return fail(e, AGAR_E_UNSUPPORTED, "pellet pool too large for this tile width%s", "");
-        int threads = 64;
+        int threads = 128;
         const char* tenv = getenv("AGAR_SIMPLE_THREADS");
         if (tenv && atoi(tenv) >= 32) threads = atoi(tenv) / 32 * 32;
-        if (threads > 64) threads = 64; /* __launch_bounds__(64, ...) */
+        if (threads > 256) threads = 256; /* __launch_bounds__(256, ...) */
+        /* measured: one CTA barrier per frame is worth 1.9x at 1M envs and 2.3x at 4096 (a warp-level barrier is
+         * worth nothing): the warps of a CTA then walk the ~5000-instruction frame body together */
+        e->sp.frame_sync = getenv("AGAR_SIMPLE_SYNC") ? atoi(getenv("AGAR_SIMPLE_SYNC")) : 1;
         size_t per_env = (size_t)e->sp.strideB;
         while (threads > 32 && per_env * (threads / W) > 200 * 1024) threads -= 32;
         e->simple_W = W;
@@ -562,7 +569,7 @@ extern "C" int agar_create(const AgarConfig* cfg, int n_envs, int device, uint64
         }
         e->init_W = 32, e->init_threads = e->threads, e->init_tiles = e->tiles, e->init_smem = e->smem_bytes;
     }
-    int W = e->full ? 32 : (n_envs <= 8192 ? 8 : (n_envs <= 32768 ? 4 : 1)); /* tools/sweep.py, profiles/r01_sweep.txt */
+    int W = e->full ? 32 : (n_envs <= 8192 ? 8 : (n_envs <= 32768 ? 2 : 1)); /* tools/sweep.py, profiles/r01_sweep.txt */
     const char* wenv = getenv("AGAR_TILE_W");
     if (wenv && atoi(wenv) > 0) W = atoi(wenv);
     if (agar_set_tile_width(e, W) != AGAR_OK && agar_set_tile_width(e, 32) != AGAR_OK) {
