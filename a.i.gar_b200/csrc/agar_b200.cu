@@ -141,6 +141,11 @@ k_main(const __grid_constant__ DevParams P, uint8_t* __restrict__ state, const f
                 c.t.sync();
             }
         }
+        if (active && c.lane == 0 && (P.turn_reward || P.turn_done))
+            for (int a = 0; a < A; ++a) {
+                if (P.turn_reward) P.turn_reward[(size_t)env * A + a] = (float)c.pl[a].bot.last_reward;
+                if (P.turn_done) P.turn_done[(size_t)env * A + a] = (uint8_t)c.pl[a].bot.exp_done;
+            }
     }
     if (P.stage == 1) stage_out(P, state, env0, n_here);
     if (P.stage == 2) {
@@ -222,7 +227,11 @@ k_simple(const __grid_constant__ DevParams P, const SimplePlan SP, uint8_t* __re
         int d_o = s_turn_begin(r, P);
         s_observe<W>(r, q, P, d_o != 0, row, sub);
     }
-    if (valid && sub == 0) s_store(r, q);
+    if (valid && sub == 0) {
+        s_store(r, q);
+        if (P.turn_reward) P.turn_reward[env] = (float)r.last_reward; /* Bot.getLastReward / done of this turn, fused */
+        if (P.turn_done) P.turn_done[env] = (uint8_t)r.exp_done;
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < n_here * tail_words; i += blockDim.x) { /* stage the pools out */
         int e = i / tail_words, w = i - e * tail_words;
@@ -360,6 +369,7 @@ struct AgarEnv {
     /* step_host staging */
     float *d_actions, *d_obs, *d_reward;
     uint8_t* d_done;
+    void* h_turn; /* pinned */
 };
 static char g_create_err[256] = "";
 
@@ -594,7 +604,7 @@ extern "C" int agar_destroy(AgarEnv* e) {
     if (e->d_actions) cudaFree(e->d_actions);
     if (e->d_obs) cudaFree(e->d_obs);
     if (e->d_reward) cudaFree(e->d_reward);
-    if (e->d_done) cudaFree(e->d_done);
+    if (e->h_turn) cudaFreeHost(e->h_turn);
     free(e);
     return AGAR_OK;
 }
@@ -677,24 +687,21 @@ extern "C" int agar_step_host(AgarEnv* e, const float* actions_host, int n_frame
     if (!e->d_actions) {
         CU(cudaMalloc(&e->d_actions, EA * 4 * sizeof(float)));
         CU(cudaMalloc(&e->d_obs, EA * e->L.state_len * sizeof(float)));
-        CU(cudaMalloc(&e->d_reward, EA * sizeof(float)));
-        CU(cudaMalloc(&e->d_done, EA));
+        CU(cudaMalloc(&e->d_reward, EA * 5)); /* packed: float reward[EA] | uint8 done[EA] -> one copy back */
+        CU(cudaMallocHost(&e->h_turn, EA * 5));
+        e->d_done = (uint8_t*)e->d_reward + EA * 4;
         CU(cudaMemsetAsync(e->d_obs, 0, EA * e->L.state_len * sizeof(float), s));
+        CU(cudaMemsetAsync(e->d_reward, 0, EA * 5, s));
     }
     CU(cudaMemcpyAsync(e->d_actions, actions_host, EA * 4 * sizeof(float), cudaMemcpyHostToDevice, s));
+    e->P.turn_reward = e->d_reward, e->P.turn_done = e->d_done; /* reward / done written by the step kernel itself */
     int rc = launch_main(e, e->d_actions, e->d_obs, n_frames, 1, KF_OBS_AFTER, 0, s);
+    e->P.turn_reward = nullptr, e->P.turn_done = nullptr;
     if (rc != AGAR_OK) return rc;
     if (obs_host) CU(cudaMemcpyAsync(obs_host, e->d_obs, EA * e->L.state_len * sizeof(float), cudaMemcpyDeviceToHost, s));
-    if (reward_host) {
-        rc = agar_get(e, AGAR_GET_REWARD, e->d_reward, s);
-        if (rc != AGAR_OK) return rc;
-        CU(cudaMemcpyAsync(reward_host, e->d_reward, EA * sizeof(float), cudaMemcpyDeviceToHost, s));
-    }
-    if (done_host) {
-        rc = agar_get(e, AGAR_GET_DONE, e->d_done, s);
-        if (rc != AGAR_OK) return rc;
-        CU(cudaMemcpyAsync(done_host, e->d_done, EA, cudaMemcpyDeviceToHost, s));
-    }
+    if (reward_host || done_host) CU(cudaMemcpyAsync(e->h_turn, e->d_reward, EA * 5, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
+    if (reward_host) memcpy(reward_host, e->h_turn, EA * 4);
+    if (done_host) memcpy(done_host, (uint8_t*)e->h_turn + EA * 4, EA);
     return AGAR_OK;
 }
