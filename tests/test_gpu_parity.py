@@ -246,3 +246,42 @@ def test_dqn_consumer_zero_copy(torch_cuda):
     for i, e in enumerate(oras):
         d = lay.compare_records(e.record, lay.Record(b.layout, st[i].copy()), what="env %d " % i)
         assert not d, d
+
+
+def test_error_behaviour(torch_cuda):
+    """The reference quit()s or raises; the ABI returns AGAR_E_* codes with a message and never falls back."""
+    import ctypes
+    from aigar_b200.env import AgarBatch, AgarError, load_library
+    lib = load_library()
+    h = ctypes.c_void_p()
+    bad = lay.derive_config(eject=True)  # eject without split: TypeError in the reference (bot.py:568)
+    assert lib.agar_create(ctypes.byref(bad), 4, 0, 0, 0, None, ctypes.byref(h)) == -4
+    assert b"rejected" in lib.agar_last_error(None)
+    cfg = lay.derive_config(grid=20)     # CNN-sized grids are a "next" row (SURVEY §8f rank 3)
+    assert lib.agar_create(ctypes.byref(cfg), 4, 0, 0, 0, None, ctypes.byref(h)) == -4
+    assert lib.agar_create(ctypes.byref(lay.derive_config()), 4, 99, 0, 0, None, ctypes.byref(h)) == -2  # no such device
+    b = AgarBatch(lay.derive_config(), 8)
+    assert lib.agar_step(b.h, None, 1, None) == -1 and b"NULL" in lib.agar_last_error(b.h)
+    with pytest.raises(AgarError):
+        b.set_tile_width(3)
+    multi = AgarBatch(lay.derive_config(num_nn=1, num_greedy=1, split=True), 4)
+    with pytest.raises(AgarError):
+        multi.set_tile_width(1)          # the register-resident kernel only covers single-cell configs
+    assert int(b.get(lay.GET_OVERFLOW).abs().sum().item()) == 0
+
+
+def test_pool_overflow_is_reported_not_ub(torch_cuda):
+    """Tiny blob / ex-blob pools: ejecting more than they hold sets the sticky overflow bits, the env keeps stepping."""
+    from aigar_b200.env import AgarBatch
+    cfg = lay.derive_config(num_nn=1, num_greedy=1, split=True, eject=True, overrides={"blob_cap": 1, "fat_cap": 1})
+    b = AgarBatch(cfg, 64, seed=3)
+    import torch
+    g = torch.Generator(device=b.device).manual_seed(0)
+    b.observe()
+    for t in range(150):
+        act = torch.rand((64, 1, 4), device=b.device, generator=g)
+        act[..., 3] = 0.9  # always eject
+        b.step_observe(act, 8)
+    ovf = b.get(lay.GET_OVERFLOW)
+    assert int((ovf != 0).sum().item()) > 0
+    assert torch.isfinite(b.get(lay.GET_MASS)).all() and (b.get(lay.GET_NCELLS) <= 16).all()
