@@ -218,9 +218,10 @@ k_simple(const __grid_constant__ DevParams P, const SimplePlan SP, uint8_t* __re
                     for (int i = 0; i < 4; ++i) act[i] = ap[i];
                 }
             }
-            s_turn_end(r, P, act);
+            double speed_pow;
+            s_turn_end<W>(r, P, act, sub, speed_pow);
             if (SP.frame_sync == 4) __syncthreads();
-            s_field_update<W>(r, q, P, env_id, sub);
+            s_field_update<W>(r, q, P, env_id, sub, speed_pow);
         }
     }
     if (flags & KF_OBS_AFTER) {

@@ -135,8 +135,36 @@ DEV void s_update_fov(SReg& r, const DevParams& P) {
     }
     r.fov_size = agar_pow(r.radius, 0.475) * P.pow_n[1] * 35;
 }
-DEV void s_set_command_point(SReg& r, const DevParams& P, double a0, double a1) { /* bot.py:550-577 */
-    s_update_fov(r, P);
+/* The two pow() of a frame — fov size (radius ^ 0.475, player.py:163-167) and speed (mass' ^ -0.35 with the mass as
+ * it will be after this frame's decay, cell.py:123-126,246-248) — have independent inputs.  With W >= 2 lanes per env
+ * the even lanes evaluate one and the odd lanes the other in the SAME instruction stream, then swap: one pow per
+ * frame instead of two (same function, same inputs: bit-identical results). */
+template <int W>
+DEV void s_dual_pow(double x0, double y0, double x1, double y1, int sub, double& p0, double& p1) {
+    if (W == 1) {
+        p0 = agar_pow(x0, y0);
+        p1 = agar_pow(x1, y1);
+        return;
+    }
+    const bool odd = (sub & 1) != 0;
+    const double mine = agar_pow(odd ? x1 : x0, odd ? y1 : y0);
+    const double other = __shfl_xor_sync(S_FULL, mine, 1);
+    p0 = odd ? other : mine;
+    p1 = odd ? mine : other;
+}
+/* bot.py:550-577 + the speed factor of the coming frame */
+template <int W>
+DEV void s_set_command_point(SReg& r, const DevParams& P, double a0, double a1, int sub, double& speed_pow) {
+    double tm = 0.0 + r.mass; /* s_update_fov, with the pow shared */
+    if (tm != 0) {
+        r.fov_x = (0.0 + r.x * r.mass) / tm;
+        r.fov_y = (0.0 + r.y * r.mass) / tm;
+        r.fov_valid = 1;
+    }
+    const double mass_next = r.mass >= 4 ? r.mass * P.decay_rate : r.mass;
+    double fov_pow;
+    s_dual_pow<W>(r.radius, 0.475, mass_next, -0.35, sub, fov_pow, speed_pow);
+    r.fov_size = fov_pow * P.pow_n[1] * 35;
     int x = (int)r.fov_x, y = (int)r.fov_y;
     int left = x - (int)(r.fov_size / 2), top = y - (int)(r.fov_size / 2);
     int size = (int)r.fov_size;
@@ -245,7 +273,7 @@ DEV void s_observe(SReg& r, const SPtr& q, const DevParams& P, bool mine, float*
 
 /* one frame of Field.update for a single-cell env (field.py:85-92); warp-uniform, state replicated per tile */
 template <int W>
-DEV void s_field_update(SReg& r, const SPtr& q, const DevParams& P, uint32_t env_id, int sub) {
+DEV void s_field_update(SReg& r, const SPtr& q, const DevParams& P, uint32_t env_id, int sub, double speed_pow) {
     const double S = (double)P.S;
     /* Player.update (player.py:30-36) */
     double mass = r.mass, radius = r.radius;
@@ -260,7 +288,7 @@ DEV void s_field_update(SReg& r, const SPtr& q, const DevParams& P, uint32_t env
     double sm = (h2 < r2 ? h2 : r2) / r2;
     double cs, sn;
     agar_dir(yd, xd, &cs, &sn);
-    double rs = P.move_speed * agar_pow(mass, -0.35);
+    double rs = P.move_speed * speed_pow; /* = agar_pow(mass, -0.35), evaluated next to the fov pow in s_turn_end */
     double vx = rs * sm * cs, vy = rs * sm * sn;
     update_pos(r.x, r.y, vx, vy, r.svx, r.svy, r.counter, S);
     r.flags |= AGAR_CF_INHASH;
@@ -404,7 +432,8 @@ DEV int s_turn_begin(SReg& r, const DevParams& P) {
     return do_obs;
 }
 /* second half of move_NN + tail of makeMove (bot.py:223-232,256-270) */
-DEV void s_turn_end(SReg& r, const DevParams& P, const float* act) {
+template <int W>
+DEV void s_turn_end(SReg& r, const DevParams& P, const float* act, int sub, double& speed_pow) {
     if (r.need_action) {
         r.cum_reward = 0;
         r.skip_frames = P.cfg.frame_skip;
@@ -419,5 +448,5 @@ DEV void s_turn_end(SReg& r, const DevParams& P, const float* act) {
         r.has_last_mass = 1;
     }
     r.turn_begun = 0;
-    s_set_command_point(r, P, r.a0, r.a1);
+    s_set_command_point<W>(r, P, r.a0, r.a1, sub, speed_pow);
 }

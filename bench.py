@@ -71,7 +71,7 @@ class ClockSampler(object):
             os.close(fd)
             self.out = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.out,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.out,
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -174,7 +174,7 @@ def workload_name(envs, frames):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--envs", type=int, default=4096)
@@ -220,11 +220,11 @@ def main():
     def one_step(i):
         batch.rollout_random(decisions, PERIOD, decision_base=i * decisions)
 
+    sampler = ClockSampler(local)  # samples from the warm-up on: the same load, more samples than the timed region alone
+    sampler.start()
     for i in range(args.warmup):
         one_step(i)
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
     launches0 = batch.launch_count
     evs = []
     barrier()
