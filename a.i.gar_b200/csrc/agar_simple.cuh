@@ -152,14 +152,32 @@ DEV void s_dual_pow(double x0, double y0, double x1, double y1, int sub, double&
     p0 = odd ? other : mine;
     p1 = odd ? mine : other;
 }
+/* a / b and c / d for the price of one division: even lanes divide one pair, odd lanes the other, then they swap */
+template <int W>
+DEV void s_dual_div(double a, double b, double c, double d, int sub, double& q0, double& q1) {
+    if (W == 1) {
+        q0 = a / b;
+        q1 = c / d;
+        return;
+    }
+    const bool odd = (sub & 1) != 0;
+    const double mine = (odd ? c : a) / (odd ? d : b);
+    const double other = __shfl_xor_sync(S_FULL, mine, 1);
+    q0 = odd ? other : mine;
+    q1 = odd ? mine : other;
+}
 /* bot.py:550-577 + the speed factor of the coming frame */
 template <int W>
 DEV void s_set_command_point(SReg& r, const DevParams& P, double a0, double a1, int sub, double& speed_pow) {
-    double tm = 0.0 + r.mass; /* s_update_fov, with the pow shared */
-    if (tm != 0) {
-        r.fov_x = (0.0 + r.x * r.mass) / tm;
-        r.fov_y = (0.0 + r.y * r.mass) / tm;
-        r.fov_valid = 1;
+    double tm = 0.0 + r.mass; /* s_update_fov, with the pow and the divisions shared across the lane pair */
+    {
+        double fx, fy;
+        s_dual_div<W>(0.0 + r.x * r.mass, tm, 0.0 + r.y * r.mass, tm, sub, fx, fy);
+        if (tm != 0) {
+            r.fov_x = fx;
+            r.fov_y = fy;
+            r.fov_valid = 1;
+        }
     }
     const double mass_next = r.mass >= 4 ? r.mass * P.decay_rate : r.mass;
     double fov_pow;
@@ -287,7 +305,14 @@ DEV void s_field_update(SReg& r, const SPtr& q, const DevParams& P, uint32_t env
     double h2 = xd * xd + yd * yd, r2 = radius * radius;
     double sm = (h2 < r2 ? h2 : r2) / r2;
     double cs, sn;
-    agar_dir(yd, xd, &cs, &sn);
+    if (h2 == 0.0) { /* agar_dir: atan2(0, 0) = 0 -> (1, 0) */
+        cs = 1.0, sn = 0.0;
+    }
+    {
+        double hh = sqrt(h2), c2, s2;
+        s_dual_div<W>(xd, hh, yd, hh, sub, c2, s2);
+        if (h2 != 0.0) cs = c2, sn = s2;
+    }
     double rs = P.move_speed * speed_pow; /* = agar_pow(mass, -0.35), evaluated next to the fov pow in s_turn_end */
     double vx = rs * sm * cs, vy = rs * sm * sn;
     update_pos(r.x, r.y, vx, vy, r.svx, r.svy, r.counter, S);
