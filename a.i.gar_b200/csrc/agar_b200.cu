@@ -488,7 +488,7 @@ extern "C" int agar_set_tile_width(AgarEnv* e, int W) {
         int tail_words = (int)((e->L.record_bytes - e->L.off_pellets) / 4);
         e->sp.strideB = (tail_words | 1) * 4;
         if (e->L.pellet_cap > 128 * W) return fail(e, AGAR_E_UNSUPPORTED, "pellet pool too large for this tile width%s", "");
-        int threads = 128;
+        int threads = e->n_envs >= 262144 ? 128 : 64; /* measured: two warps per CTA below ~256k envs, four above */
         const char* tenv = getenv("AGAR_SIMPLE_THREADS");
         if (tenv && atoi(tenv) >= 32) threads = atoi(tenv) / 32 * 32;
         if (threads > 256) threads = 256; /* __launch_bounds__(256, ...) */
