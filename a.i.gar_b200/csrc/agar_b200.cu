@@ -497,6 +497,8 @@ extern "C" int agar_set_tile_width(AgarEnv* e, int W) {
         e->sp.frame_sync = getenv("AGAR_SIMPLE_SYNC") ? atoi(getenv("AGAR_SIMPLE_SYNC")) : 1;
         size_t per_env = (size_t)e->sp.strideB;
         while (threads > 32 && per_env * (threads / W) > 200 * 1024) threads -= 32;
+        if (per_env * (threads / W) > 200 * 1024)
+            return fail(e, AGAR_E_NOMEM, "pellet pool + event ring of %s do not fit in shared memory at this tile width", "the envs of one CTA");
         e->simple_W = W;
         e->simple_threads = threads;
         e->simple_smem = per_env * (threads / W);
@@ -583,7 +585,7 @@ extern "C" int agar_create(const AgarConfig* cfg, int n_envs, int device, uint64
     int W = e->full ? 32 : (n_envs <= 8192 ? 8 : (n_envs <= 32768 ? 2 : 1)); /* tools/sweep.py, profiles/r01_sweep.txt */
     const char* wenv = getenv("AGAR_TILE_W");
     if (wenv && atoi(wenv) > 0) W = atoi(wenv);
-    if (agar_set_tile_width(e, W) != AGAR_OK && agar_set_tile_width(e, 32) != AGAR_OK) {
+    if (agar_set_tile_width(e, W) != AGAR_OK && agar_set_tile_width(e, 8) != AGAR_OK && agar_set_tile_width(e, 32) != AGAR_OK) {
         strncpy(g_create_err, e->err, 255);
         cudaFree(e->state), cudaFree(e->deg_tab), free(e);
         return AGAR_E_NOMEM;

@@ -268,6 +268,11 @@ def test_error_behaviour(torch_cuda):
     with pytest.raises(AgarError):
         multi.set_tile_width(1)          # the register-resident kernel only covers single-cell configs
     assert int(b.get(lay.GET_OVERFLOW).abs().sum().item()) == 0
+    big = AgarBatch(lay.derive_config(event_cap=512), 64)   # a 10 KB event ring per env: one lane per env cannot hold 32 of them
+    with pytest.raises(AgarError):
+        big.set_tile_width(1)
+    big.set_tile_width(8)
+    big.rollout_random(2, 8, 0)
 
 
 def test_pool_overflow_is_reported_not_ub(torch_cuda):
