@@ -123,6 +123,30 @@ DEV void axis_buckets2(double p, double radius, double fov, double gs, double in
     b0 = x0 <= lim ? c0 : -1;
     b1 = (x1 <= lim && c1 != c0) ? c1 : -1; /* ids is a set */
 }
+/* axis_buckets2 with the edge lookups from a per-observation bit table: for x0 = q * gs, int(x0 / gs) is q or q - 1, and
+ * for x1 = x0 + gs, int(x1 / gs) is q + 1 or q — both depend on q only.  bit q of `edges`: x0 falls to q - 1;
+ * bit 16 + q: x1 falls to q.  (built by edge_bits() once per observation) */
+DEV unsigned edge_bits(double gs, double inv, int G) {
+    unsigned m = 0;
+    for (int k = 0; k <= G; ++k) {
+        double x0 = (double)k * gs, x1 = x0 + gs;
+        if (bucket_of_edge(x0, gs, inv) != k) m |= 1u << k;
+        if (bucket_of_edge(x1, gs, inv) != k + 1) m |= 1u << (16 + k);
+    }
+    return m;
+}
+DEV void axis_buckets2_bits(double p, double radius, double fov, double gs, double inv, unsigned edges, int& b0, int& b1) {
+    double cl = py_max0(p - radius);
+    double q = floor(cl * inv);
+    double res = fma(-q, gs, cl);
+    q = res < 0 ? q - 1 : (res >= gs ? q + 1 : q);
+    const double x0 = q * gs, x1 = x0 + gs;
+    const double lim = (p + radius < fov - 1) ? p + radius : fov - 1;
+    const int iq = (int)q;
+    const int c0 = iq - (int)((edges >> iq) & 1u), c1 = iq + 1 - (int)((edges >> (16 + iq)) & 1u);
+    b0 = x0 <= lim ? c0 : -1;
+    b1 = (x1 <= lim && c1 != c0) ? c1 : -1;
+}
 /* calls f(id) once per distinct bucket of the object (ids is a set in the reference) */
 template <class F>
 DEV void for_each_fov_bucket(double ox, double oy, double radius, double left, double top, double fov, double gs,

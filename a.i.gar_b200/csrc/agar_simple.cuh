@@ -255,6 +255,8 @@ DEV void s_observe(SReg& r, const SPtr& q, const DevParams& P, bool mine, float*
         /* phase 2: every lane bins its own next candidate per iteration.  The body is straight-line (predicated REDs,
          * two-bucket axis form), so the lanes of a warp stay converged until the longest list ends. */
         const bool sheared = cols != G;
+        const bool use_bits = W <= 2 && !canon && G <= 15; /* 2 (G + 1) edge evaluations per observation instead of 4 per pellet */
+        const unsigned edges = use_bits ? edge_bits(gs, inv, G) : 0u;
         while (m0 | m1) {
             int j;
             if (m0) {
@@ -270,8 +272,13 @@ DEV void s_observe(SReg& r, const SPtr& q, const DevParams& P, bool mine, float*
             double dx = (double)px, dy = (double)py;
             bool ok = rect_hit(ra, pellet_rect(px, py)) && !(dx + pr < xmin || dx - pr > xmax || dy + pr < ymin || dy - pr > ymax);
             int c0, c1, r0, r1;
-            axis_buckets2(dx - left, pr, fov, gs, inv, canon, c0, c1);
-            axis_buckets2(dy - top, pr, fov, gs, inv, canon, r0, r1);
+            if (use_bits) {
+                axis_buckets2_bits(dx - left, pr, fov, gs, inv, edges, c0, c1);
+                axis_buckets2_bits(dy - top, pr, fov, gs, inv, edges, r0, r1);
+            } else {
+                axis_buckets2(dx - left, pr, fov, gs, inv, canon, c0, c1);
+                axis_buckets2(dy - top, pr, fov, gs, inv, canon, r0, r1);
+            }
             float fm = (float)pm;
             auto put = [&](int cc, int rr) {
                 /* bucket id = cc + rr * cols is read by square (id / G, id % G).  cols == G: that is (rr, cc); cols == G + 1

@@ -1,0 +1,31 @@
+"""bench.py's CPU-runnable leg (--impl reference: the oracle port on the host cores) prints one JSON line with the
+contract's keys; the GPU leg refuses to run without a device instead of falling back."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--envs", "64", "--frames", "80"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-500:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["metric"] == "env_steps_per_sec" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_gpu_arm_has_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("GPU present")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"], capture_output=True,
+                         text=True, timeout=300, cwd=ROOT)
+    assert out.returncode != 0 and "no CUDA device" in (out.stderr + out.stdout)

@@ -290,3 +290,18 @@ def test_pool_overflow_is_reported_not_ub(torch_cuda):
     ovf = b.get(lay.GET_OVERFLOW)
     assert int((ovf != 0).sum().item()) > 0
     assert torch.isfinite(b.get(lay.GET_MASS)).all() and (b.get(lay.GET_NCELLS) <= 16).all()
+
+
+def test_debug_dump_and_load_roundtrip(torch_cuda):
+    """agar_debug_dump / agar_debug_load: a record moved into another handle (other env slot, other global id) steps
+    identically once the Philox key matches — the record is the whole state."""
+    cfg = lay.derive_config(num_nn=1, num_greedy=1, virus=True, split=True, eject=True)
+    a = _batch(cfg, 4, seed=6, first_env_id=10)
+    a.rollout_random(6, 8, 0)
+    rec = a.dump(2)                      # global env id 12
+    b = _batch(cfg, 3, seed=6, first_env_id=12)
+    b.load(0, rec)                       # slot 0 of b has global id 12 as well
+    a.rollout_random(4, 8, 6)
+    b.rollout_random(4, 8, 6)
+    d = lay.compare_records(a.dump(2), b.dump(0))
+    assert not d, d
