@@ -370,9 +370,10 @@ DEV double bot_reward(const Ctx<W>& c, const DevParams& P, int k) {
 }
 /* lane 0; set_command_point bot.py:550-577 + Player.setCommands */
 template <int W>
-DEV void set_command_point(Ctx<W>& c, const DevParams& P, int k, double a0, double a1, double a2, double a3, int len) {
+DEV void set_command_point(Ctx<W>& c, const DevParams& P, int k, double a0, double a1, double a2, double a3, int len,
+                           bool fov_fresh) {
     AgarPlayer* p = &c.pl[k];
-    update_fov(c, P, k);
+    if (!fov_fresh) update_fov(c, P, k); /* fresh: computed a moment ago in this bot turn from the same cells */
     int x = (int)p->fov_x, y = (int)p->fov_y;
     int left = x - (int)(p->fov_size / 2), top = y - (int)(p->fov_size / 2);
     int size = (int)p->fov_size;
@@ -447,7 +448,7 @@ DEV void nn_turn_end(Ctx<W>& c, const DevParams& P, int k, const float* action) 
     int len = P.L.action_len;
     double a2 = B->cur_action[2], a3 = B->cur_action[3];
     if (B->skipping) a2 = a3 = 0, len = 4;
-    set_command_point(c, P, k, B->cur_action[0], B->cur_action[1], a2, a3, len);
+    set_command_point(c, P, k, B->cur_action[0], B->cur_action[1], a2, a3, len, B->need_action != 0 /* observed this turn */);
 }
 
 /* cooperative; make_greedy_bot_move bot.py:579-633 / make_random_bot_move :243-249 */
@@ -548,7 +549,7 @@ DEV void scripted_turn(Ctx<W>& c, const DevParams& P, int k) {
     }
     if (c.lane == 0) {
         B->has_action = 1;
-        set_command_point(c, P, k, B->cur_action[0], B->cur_action[1], B->cur_action[2], B->cur_action[3], 4);
+        set_command_point(c, P, k, B->cur_action[0], B->cur_action[1], B->cur_action[2], B->cur_action[3], 4, true);
     }
     c.t.sync();
 }
