@@ -39,14 +39,18 @@ __device__ __forceinline__ void stage_out(const DevParams& P, uint8_t* state, in
         dst[i] = ((const uint2*)(g_smem + (size_t)e * P.rec_stride))[w];
     }
 }
-__device__ __forceinline__ int pel_cache_bytes(const DevParams& P) { return (P.L.pellet_cap * 4 + 15) / 16 * 16; }
-/* stage == 2: copy the pellet pools of this CTA's envs between HBM and their shared-memory cache */
+/* stage >= 2 ("hot sections"): big records stay in HBM / L2; what every scan and every lane-0 step reads is cached in
+ * shared memory — the pellet pool, and with hot_a > 0 also bytes [0, hot_a) = header, players, cells, viruses */
+__device__ __forceinline__ int hot_a_bytes(const DevParams& P) { return (P.hot_a + 15) / 16 * 16; }
+__device__ __forceinline__ int pel_cache_bytes(const DevParams& P) { return hot_a_bytes(P) + (P.L.pellet_cap * 4 + 15) / 16 * 16; }
 __device__ __forceinline__ void pel_cache_copy(const DevParams& P, uint8_t* state, int env0, int n_here, int tiles, bool in) {
-    const int words = P.L.pellet_cap;
+    const int wa = P.hot_a / 4, words = wa + P.L.pellet_cap;
     for (int i = threadIdx.x; i < n_here * words; i += blockDim.x) {
         int e = i / words, w = i - e * words;
-        uint32_t* g = (uint32_t*)(state + (size_t)(env0 + e) * P.L.record_bytes + P.L.off_pellets) + w;
-        uint32_t* s = (uint32_t*)(g_smem + (size_t)tiles * P.scratch_bytes + (size_t)e * pel_cache_bytes(P)) + w;
+        uint8_t* rec = state + (size_t)(env0 + e) * P.L.record_bytes;
+        uint8_t* hot = g_smem + (size_t)tiles * P.scratch_bytes + (size_t)e * pel_cache_bytes(P);
+        uint32_t* g = w < wa ? (uint32_t*)rec + w : (uint32_t*)(rec + P.L.off_pellets) + (w - wa);
+        uint32_t* s = w < wa ? (uint32_t*)hot + w : (uint32_t*)(hot + hot_a_bytes(P)) + (w - wa);
         if (in) *s = *g; else *g = *s;
     }
     __syncthreads();
@@ -66,8 +70,16 @@ __device__ __forceinline__ void bind_ctx(Ctx<W>& c, const DevParams& P, int tile
     c.hist = (float*)(c.rec + P.L.off_hist);
     c.ev = (AgarEvent*)(c.rec + P.L.off_events);
     c.scratch = g_smem + (P.stage == 1 ? (size_t)tiles * P.rec_stride : 0) + (size_t)tile_id * P.scratch_bytes;
-    if (P.stage == 2) /* big records stay in HBM / L2; only the pellet pool — what every scan reads — is cached on chip */
-        c.pel = (uint32_t*)(g_smem + (size_t)tiles * P.scratch_bytes + (size_t)tile_id * pel_cache_bytes(P));
+    if (P.stage >= 2) {
+        uint8_t* hot = g_smem + (size_t)tiles * P.scratch_bytes + (size_t)tile_id * pel_cache_bytes(P);
+        c.pel = (uint32_t*)(hot + hot_a_bytes(P));
+        if (P.hot_a > 0) { /* header .. viruses are contiguous from byte 0 of the record */
+            c.h = (AgarEnvHeader*)(hot + P.L.off_header);
+            c.pl = (AgarPlayer*)(hot + P.L.off_players);
+            c.cells = (AgarCell*)(hot + P.L.off_cells);
+            c.vir = (AgarMote*)(hot + P.L.off_viruses);
+        }
+    }
 }
 
 /* ------------------------------------------------------------------ the step kernel */
@@ -79,7 +91,7 @@ k_main(const __grid_constant__ DevParams P, uint8_t* __restrict__ state, const f
     const int env0 = blockIdx.x * tiles;
     const int n_here = min(tiles, P.n_envs - env0);
     if (P.stage == 1) stage_in(P, state, env0, n_here, false);
-    if (P.stage == 2) pel_cache_copy(P, state, env0, n_here, tiles, true);
+    if (P.stage >= 2) pel_cache_copy(P, state, env0, n_here, tiles, true);
     const int tile_id = threadIdx.x / W;
     const bool active = tile_id < n_here;
     {
@@ -148,7 +160,7 @@ k_main(const __grid_constant__ DevParams P, uint8_t* __restrict__ state, const f
             }
     }
     if (P.stage == 1) stage_out(P, state, env0, n_here);
-    if (P.stage == 2) {
+    if (P.stage >= 2) {
         __syncthreads();
         pel_cache_copy(P, state, env0, n_here, tiles, false);
     }
@@ -257,7 +269,7 @@ k_init(const __grid_constant__ DevParams P, uint8_t* __restrict__ state, const u
         for (int i = threadIdx.x; i < n_here * chunks; i += blockDim.x) dst[i] = make_uint2(0u, 0u);
         __syncthreads();
     }
-    if (P.stage == 2) pel_cache_copy(P, state, env0, n_here, tiles, true);
+    if (P.stage >= 2) pel_cache_copy(P, state, env0, n_here, tiles, true);
     const int tile_id = threadIdx.x / W;
     if (tile_id < n_here && (mask == nullptr || mode == 0 || mask[env0 + tile_id])) {
         Ctx<W> c(cg::tiled_partition<W>(cg::this_thread_block()));
@@ -310,7 +322,7 @@ k_init(const __grid_constant__ DevParams P, uint8_t* __restrict__ state, const u
         }
     }
     if (P.stage == 1) stage_out(P, state, env0, n_here);
-    if (P.stage == 2) {
+    if (P.stage >= 2) {
         __syncthreads();
         pel_cache_copy(P, state, env0, n_here, tiles, false);
     }
@@ -401,7 +413,7 @@ static bool config_is_simple(const AgarConfig& c, const AgarLayout& L) {
 static bool plan_launch(AgarEnv* e, int W) {
     const size_t budget = 200 * 1024;
     size_t per_tile = (e->P.stage == 1 ? (size_t)e->P.rec_stride : 0) + (size_t)e->P.scratch_bytes +
-                      (e->P.stage == 2 ? (size_t)((e->L.pellet_cap * 4 + 15) / 16 * 16) : 0);
+                      (e->P.stage >= 2 ? (size_t)((e->P.hot_a + 15) / 16 * 16) + (size_t)((e->L.pellet_cap * 4 + 15) / 16 * 16) : 0);
     int tiles = e->full ? 512 / W : 128 / W; /* as many envs per CTA as fit: the barriers then align more warps */
     if (getenv("AGAR_MAX_TILES")) tiles = atoi(getenv("AGAR_MAX_TILES"));
     if (tiles * W > 512) tiles = 512 / W;
@@ -541,15 +553,24 @@ extern "C" int agar_create(const AgarConfig* cfg, int n_envs, int device, uint64
     P.n_envs = n_envs;
     P.rec_stride = (int)L.record_bytes + 8;
     P.full = e->full;
-    /* small records are stepped in shared memory; big ones (multi-agent arenas: 60 KB) in place through L1 / L2,
-     * which keeps >= 32 warps per SM resident instead of 3 (profiles/r01_sweep_full.txt) */
-    P.stage = L.record_bytes <= 16 * 1024 ? 1 : 2; /* 2: only the pellet pool is cached in shared memory */
-    if (getenv("AGAR_STAGE")) P.stage = atoi(getenv("AGAR_STAGE"));
-    /* multi-agent kernels are instruction-fetch bound: lock-step the CTA's warps phase by phase (measured 2x) */
-    P.phase_sync = getenv("AGAR_PHASE_SYNC") ? atoi(getenv("AGAR_PHASE_SYNC")) : e->full;
     int vel_bytes = e->full ? L.n_players * L.cell_cap * 2 * 8 : 0;
     int obs_bytes = obs_scratch_bytes(L.grid_squares, e->full != 0);
     P.scratch_bytes = ((vel_bytes > obs_bytes ? vel_bytes : obs_bytes) + 15) / 16 * 16 + 8;
+    /* Where a record lives during a launch.  1: whole record staged in shared memory (single-cell general kernel).
+     * Multi-agent configs keep the record in HBM / L2 and cache on chip what every scan and lane-0 step reads:
+     * 3 = header + players + cells + viruses + pellet pool if at least 12 envs per CTA still fit, else 2 = the pellet
+     * pool only (the 16-player arena: 23 KB of cells).  Measured (profiles/r01_sweep.txt): config 3 6.3e7 / 7.3e7 /
+     * 7.7e7 env-steps/s for 1 / 2 / 3; config 4 0.75e6 (1, 3 warps per SM) / 3.3e6 (2) / 1.6e6 (3). */
+    if (!e->full)
+        P.stage = 1;
+    else {
+        size_t hot3 = (size_t)((L.off_blobs + 15) / 16 * 16) + (size_t)((L.pellet_cap * 4 + 15) / 16 * 16) + P.scratch_bytes;
+        P.stage = hot3 * 12 <= 200 * 1024 ? 3 : 2;
+    }
+    if (getenv("AGAR_STAGE")) P.stage = atoi(getenv("AGAR_STAGE"));
+    P.hot_a = P.stage == 3 ? (int)L.off_blobs : 0;
+    /* multi-agent kernels are instruction-fetch bound: lock-step the CTA's warps phase by phase (measured 2x) */
+    P.phase_sync = getenv("AGAR_PHASE_SYNC") ? atoi(getenv("AGAR_PHASE_SYNC")) : e->full;
     double speed_modifier = 1.0 / 30;
     P.move_speed = 90 * speed_modifier;
     P.decay_rate = 1 - (0.01 * speed_modifier);

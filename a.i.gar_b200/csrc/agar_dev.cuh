@@ -44,6 +44,7 @@ struct DevParams {
     double pow_n[17];
     const double* deg_tab; /* cos(d*pi/180)[360], sin(...)[360] — host libm, exactly the oracle's table */
     uint64_t seed, first_env;
+    int hot_a, pad2; /* stage >= 2: bytes [0, hot_a) of a record (header, players, cells, viruses) are cached in shared memory too */
     /* optional per-launch outputs of the last bot turn ([E][A]); NULL = use agar_get */
     float* turn_reward;
     uint8_t* turn_done;
