@@ -305,3 +305,15 @@ def test_debug_dump_and_load_roundtrip(torch_cuda):
     b.rollout_random(4, 8, 6)
     d = lay.compare_records(a.dump(2), b.dump(0))
     assert not d, d
+
+
+def test_general_kernel_on_the_single_cell_config(torch_cuda):
+    """AGAR_GENERAL_KERNEL=1 routes the pellet-collection config through k_main<32,false> (whole record staged in shared
+    memory) instead of k_simple: the two kernels are bit-identical, both equal the oracle."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, AGAR_GENERAL_KERNEL="1")
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "gpu_check.py"), "1", "24", "160", "32"], env=env,
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "bit-exact (W=32)" in out.stdout, out.stdout[-800:] + out.stderr[-400:]
