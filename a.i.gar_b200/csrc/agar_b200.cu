@@ -383,6 +383,7 @@ struct AgarEnv {
     float *d_actions, *d_obs, *d_reward;
     uint8_t* d_done;
     void* h_turn; /* pinned */
+    long long attr_main, attr_simple; /* launch shapes whose max-dynamic-shared-memory attribute is already set */
 };
 static char g_create_err[256] = "";
 
@@ -430,8 +431,12 @@ static bool plan_launch(AgarEnv* e, int W) {
 template <int W, bool FULL>
 static cudaError_t launch_main_t(AgarEnv* e, const float* actions, float* obs, int n_frames, int n_dec, int flags,
                                  uint32_t dec_base, cudaStream_t s) {
-    cudaError_t err = cudaFuncSetAttribute(k_main<W, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes);
-    if (err != cudaSuccess) return err;
+    cudaError_t err = cudaSuccess;
+    if (e->attr_main != (long long)W * (1ll << 32) + (long long)e->smem_bytes) { /* once per launch shape, not per launch */
+        err = cudaFuncSetAttribute(k_main<W, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes);
+        if (err != cudaSuccess) return err;
+        e->attr_main = (long long)W * (1ll << 32) + (long long)e->smem_bytes;
+    }
     int blocks = (e->n_envs + e->tiles - 1) / e->tiles;
     k_main<W, FULL><<<blocks, e->threads, e->smem_bytes, s>>>(e->P, e->state, actions, obs, n_frames, n_dec, flags, dec_base);
     return cudaGetLastError();
@@ -461,7 +466,11 @@ static int launch_main(AgarEnv* e, const float* actions, float* obs, int n_frame
         int blocks = (e->n_envs * e->simple_W + e->simple_threads - 1) / e->simple_threads;
 #define LAUNCH_SIMPLE(WW)                                                                                                     \
     do {                                                                                                                      \
-        err = cudaFuncSetAttribute(k_simple<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->simple_smem);           \
+        err = cudaSuccess;                                                                                                    \
+        if (e->attr_simple != (long long)WW * (1ll << 32) + (long long)e->simple_smem) {                                      \
+            err = cudaFuncSetAttribute(k_simple<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->simple_smem);       \
+            if (err == cudaSuccess) e->attr_simple = (long long)WW * (1ll << 32) + (long long)e->simple_smem;                 \
+        }                                                                                                                     \
         if (err == cudaSuccess) {                                                                                             \
             k_simple<WW><<<blocks, e->simple_threads, e->simple_smem, (cudaStream_t)stream>>>(e->P, e->sp, e->state, actions, obs, \
                                                                                               n_frames, n_dec, flags, dec_base);  \

@@ -87,7 +87,27 @@ class DQNDriver(object):
         actions = self.decide()
         self.batch.step_observe(actions, self.period)
 
-    def run(self, n_decisions):
+    def run(self, n_decisions, use_graph=False):
+        """n_decisions collector ticks.  use_graph: capture one tick (MLP + arg-max + table lookup + our step kernel, all on
+        one stream, no host synchronisation inside) into a CUDA graph and replay it — the tick is launch-bound below ~100k
+        envs."""
+        torch = self.torch
         self.batch.observe()
-        for _ in range(n_decisions):
-            self.tick()
+        if not use_graph or self.epsilon > 0:
+            for _ in range(n_decisions):
+                self.tick()
+            return
+        if getattr(self, "_graph", None) is None:
+            side = torch.cuda.Stream(device=self.batch.device)
+            side.wait_stream(torch.cuda.current_stream(self.batch.device))
+            with torch.cuda.stream(side):  # warm-up outside capture (lazy cuBLAS / attribute initialisation)
+                self.tick()
+                self.tick()
+            torch.cuda.current_stream(self.batch.device).wait_stream(side)
+            torch.cuda.synchronize(self.batch.device)
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self.tick()
+            n_decisions -= 2  # the two warm-up ticks advanced the envs (capturing records, it does not execute)
+        for _ in range(max(n_decisions, 0)):
+            self._graph.replay()

@@ -320,7 +320,16 @@ def main():
             e.record()
             torch.cuda.synchronize()
             ms = s.elapsed_time(e)
+            drv.run(4, use_graph=True)  # capture one tick into a CUDA graph, then time replays
+            torch.cuda.synchronize()
+            s.record()
+            for _ in range(ticks):
+                drv._graph.replay()
+            e.record()
+            torch.cuda.synchronize()
+            ms_g = s.elapsed_time(e)
             extra["dqn_65536"] = {"value": E3 * ticks * PERIOD / (ms * 1e-3), "unit": UNIT, "ms_per_tick": ms / ticks,
+                                  "value_cuda_graph": E3 * ticks * PERIOD / (ms_g * 1e-3), "ms_per_tick_cuda_graph": ms_g / ticks,
                                   "policy": "torch MLP 123-100-100-25 (fp32), arg-max, 5x5 action table; obs via DLPack",
                                   "tile_width": b3.tile_width}
             b3.close()

@@ -317,3 +317,16 @@ def test_general_kernel_on_the_single_cell_config(torch_cuda):
     out = subprocess.run([sys.executable, os.path.join(root, "tools", "gpu_check.py"), "1", "24", "160", "32"], env=env,
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "bit-exact (W=32)" in out.stdout, out.stdout[-800:] + out.stderr[-400:]
+
+
+def test_dqn_tick_in_a_cuda_graph(torch_cuda):
+    """The collector tick (MLP -> arg-max -> table -> agar_step_observe) captured in a CUDA graph replays to the same
+    env states as the eager loop: nothing in the C ABI synchronises the host on the step path."""
+    from aigar_b200.dqn import DQNDriver
+    cfg = lay.derive_config()
+    a, b = _batch(cfg, 512, seed=12), _batch(cfg, 512, seed=12)
+    da, db = DQNDriver(a, seed=3), DQNDriver(b, seed=3)
+    da.run(10)
+    db.run(10, use_graph=True)
+    torch_cuda.cuda.synchronize()
+    assert torch_cuda.equal(a.state_tensor(), b.state_tensor()) and torch_cuda.equal(a.obs, b.obs)
