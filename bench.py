@@ -306,6 +306,29 @@ def main():
             b2.close()
         except Exception as ex:  # never lose the headline line to the side measurement
             extra["envs_262144"] = {"error": str(ex)[:200]}
+        try:  # the same workload with an observation EVERY frame (FRAME_SKIP_RATE = 0 -> 1672 B per env-step)
+            cfg0 = lay.derive_config(frame_skip=0)
+            b0 = AgarBatch(cfg0, E, device=local, seed=2026, first_env_id=5 * 10 ** 6)
+            for i in range(3):
+                b0.rollout_random(frames, 1, decision_base=i * frames)
+            ts = []
+            for i in range(5):
+                flush.fill_(i)
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                b0.rollout_random(frames, 1, decision_base=(3 + i) * frames)
+                e.record()
+                torch.cuda.synchronize()
+                ts.append(s.elapsed_time(e))
+            ms = sum(ts) / len(ts)
+            v0 = E * frames / (ms * 1e-3)
+            peak, _ = measured_peak()
+            extra["obs_every_frame"] = {"value": v0, "unit": UNIT, "ms_per_launch": ms, "bytes_per_env_step": algorithmic_bytes_per_env_step(obs_per_frame=1.0),
+                                        "roofline_frac": v0 * algorithmic_bytes_per_env_step(obs_per_frame=1.0) / 1e9 / peak,
+                                        "tile_width": b0.tile_width}
+            b0.close()
+        except Exception as ex:
+            extra["obs_every_frame"] = {"error": str(ex)[:200]}
         try:  # BASELINE configs[4] shard: obs -> DLPack -> torch DQN forward -> arg-max -> 5x5 table -> 8 frames
             from aigar_b200.dqn import DQNDriver
             E3, ticks = 65536, 20
