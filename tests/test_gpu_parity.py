@@ -330,3 +330,33 @@ def test_dqn_tick_in_a_cuda_graph(torch_cuda):
     db.run(10, use_graph=True)
     torch_cuda.cuda.synchronize()
     assert torch_cuda.equal(a.state_tensor(), b.state_tensor()) and torch_cuda.equal(a.obs, b.obs)
+
+
+def test_batched_td_targets_equal_the_reference_loop(torch_cuda):
+    """learner.DQNLearner.targets_and_td == the per-sample loop of src/model/qLearning.py:114-127,146-185."""
+    torch = torch_cuda
+    from aigar_b200.dqn import make_dqn
+    from aigar_b200.learner import DQNLearner
+    net = make_dqn(123, device="cuda", seed=2)
+    lrn = DQNLearner(net, discount=0.9)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    B = 64
+    s = torch.rand((B, 123), device="cuda", generator=g)
+    s2 = torch.rand((B, 123), device="cuda", generator=g)
+    a = torch.randint(0, 25, (B,), device="cuda", generator=g)
+    r = torch.randn((B,), device="cuda", generator=g)
+    d = (torch.rand((B,), device="cuda", generator=g) < 0.2).to(torch.uint8)
+    targets, td = lrn.targets_and_td(s, a, r, s2, d)
+    with torch.no_grad():
+        q_old, q_new = net(s).cpu().numpy(), lrn.target(s2).cpu().numpy()
+    for i in range(B):  # calculateTarget / calculateTargetForAction, sample by sample
+        target = float(r[i])
+        if int(d[i]) == 0:
+            target += 0.9 * q_new[i][int(np.argmax(q_new[i]))]
+        old = q_old[i].copy()
+        td_e = target - old[int(a[i])]
+        old[int(a[i])] = target
+        np.testing.assert_allclose(targets[i].cpu().numpy(), old, rtol=1e-5, atol=1e-6)
+        assert abs(float(td[i]) - td_e) < 1e-5
+    td2, loss = lrn.learn(s, a, r, s2, d, torch.ones(B, device="cuda"))
+    assert np.isfinite(loss) and td2.shape == (B,)
