@@ -383,6 +383,7 @@ struct AgarEnv {
     float *d_actions, *d_obs, *d_reward;
     uint8_t* d_done;
     void* h_turn; /* pinned */
+    int host_pending; /* agar_step_host_begin issued, _end not yet */
     long long attr_main, attr_simple; /* launch shapes whose max-dynamic-shared-memory attribute is already set */
 };
 static char g_create_err[256] = "";
@@ -505,7 +506,9 @@ static int launch_init(AgarEnv* e, const uint8_t* mask, int mode, void* stream) 
  * (agar_simple.cuh), 16 / 32 the general kernel; every other config: 4, 8, 16, 32 (general kernel). */
 extern "C" int agar_set_tile_width(AgarEnv* e, int W) {
     if (!e) return AGAR_E_INVALID;
-    if (!e->full && (W == 1 || W == 2 || W == 4 || W == 8 || W == 16 || W == 32) && !getenv("AGAR_GENERAL_KERNEL")) {
+    /* the register-resident kernel bins a pellet into at most two squares per axis: 2 * radius < fov / G needs G <= 16 */
+    if (!e->full && e->L.grid_squares <= 16 && (W == 1 || W == 2 || W == 4 || W == 8 || W == 16 || W == 32) &&
+        !getenv("AGAR_GENERAL_KERNEL")) {
         int tail_words = (int)((e->L.record_bytes - e->L.off_pellets) / 4);
         e->sp.strideB = (tail_words | 1) * 4;
         if (e->L.pellet_cap > 128 * W) return fail(e, AGAR_E_UNSUPPORTED, "pellet pool too large for this tile width%s", "");
@@ -541,7 +544,6 @@ extern "C" int agar_create(const AgarConfig* cfg, int n_envs, int device, uint64
     AgarLayout L;
     int rc = agar_layout_compute(cfg, &L);
     if (rc != AGAR_OK) return fail(nullptr, rc, "config rejected by agar_layout_compute%s", "");
-    if (cfg->grid_squares > 16) return fail(nullptr, AGAR_E_UNSUPPORTED, "grid_squares > 16 not supported yet%s", "");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
         return fail(nullptr, AGAR_E_CUDA, "no such CUDA device%s", "");
@@ -710,8 +712,7 @@ extern "C" int agar_debug_load(AgarEnv* e, int env_index, const void* record_hos
     CU(cudaStreamSynchronize((cudaStream_t)stream));
     return AGAR_OK;
 }
-extern "C" int agar_step_host(AgarEnv* e, const float* actions_host, int n_frames, float* obs_host, float* reward_host,
-                              uint8_t* done_host, void* stream) {
+extern "C" int agar_step_host_begin(AgarEnv* e, const float* actions_host, int n_frames, float* obs_host, void* stream) {
     AgarEnv* env = e;
     if (!e || !actions_host || n_frames < 0) return AGAR_E_INVALID;
     CU(cudaSetDevice(e->device));
@@ -732,9 +733,26 @@ extern "C" int agar_step_host(AgarEnv* e, const float* actions_host, int n_frame
     e->P.turn_reward = nullptr, e->P.turn_done = nullptr;
     if (rc != AGAR_OK) return rc;
     if (obs_host) CU(cudaMemcpyAsync(obs_host, e->d_obs, EA * e->L.state_len * sizeof(float), cudaMemcpyDeviceToHost, s));
-    if (reward_host || done_host) CU(cudaMemcpyAsync(e->h_turn, e->d_reward, EA * 5, cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
+    CU(cudaMemcpyAsync(e->h_turn, e->d_reward, EA * 5, cudaMemcpyDeviceToHost, s));
+    e->host_pending = 1;
+    return AGAR_OK;
+}
+
+extern "C" int agar_step_host_end(AgarEnv* e, float* reward_host, uint8_t* done_host, void* stream) {
+    AgarEnv* env = e;
+    if (!e) return AGAR_E_INVALID;
+    if (!e->host_pending) return fail(env, AGAR_E_INVALID, "%s", "agar_step_host_end without agar_step_host_begin");
+    CU(cudaSetDevice(e->device));
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    e->host_pending = 0;
+    const size_t EA = (size_t)e->n_envs * (e->L.n_agents ? e->L.n_agents : 1);
     if (reward_host) memcpy(reward_host, e->h_turn, EA * 4);
     if (done_host) memcpy(done_host, (uint8_t*)e->h_turn + EA * 4, EA);
     return AGAR_OK;
+}
+
+extern "C" int agar_step_host(AgarEnv* e, const float* actions_host, int n_frames, float* obs_host, float* reward_host,
+                              uint8_t* done_host, void* stream) {
+    int rc = agar_step_host_begin(e, actions_host, n_frames, obs_host, stream);
+    return rc != AGAR_OK ? rc : agar_step_host_end(e, reward_host, done_host, stream);
 }

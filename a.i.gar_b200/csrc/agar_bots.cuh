@@ -55,13 +55,14 @@ DEV int exact_floor_div(double v, double gs, double inv) {
     q = res < 0 ? q - 1 : (res >= gs ? q + 1 : q);
     return (int)q;
 }
-DEV unsigned axis_buckets(double p, double radius, double fov, double gs, double inv, bool canon) {
+/* columns as a 64-bit mask: G <= 63, cols <= 64 (agar_layout.h) */
+DEV unsigned long long axis_buckets(double p, double radius, double fov, double gs, double inv, bool canon) {
     if (canon) { /* AGAR_OBS_CANONICAL: buckets floor(lo / gs) .. floor(hi / gs) with exact floors */
         double lo = py_max0(p - radius), hi = (p + radius < fov - 1) ? p + radius : fov - 1;
-        if (hi < 0) return 0u;
+        if (hi < 0) return 0ull;
         int b0 = exact_floor_div(lo, gs, inv), b1 = exact_floor_div(hi, gs, inv);
-        if (b1 < b0) return 0u;
-        return (b1 >= 31 ? 0xffffffffu : ((2u << b1) - 1)) & ~((1u << b0) - 1);
+        if (b1 < b0) return 0ull;
+        return (b1 >= 63 ? ~0ull : ((2ull << b1) - 1)) & ~((1ull << b0) - 1);
     }
     double cl = py_max0(p - radius);
     double q = floor(cl * inv);
@@ -72,7 +73,7 @@ DEV unsigned axis_buckets(double p, double radius, double fov, double gs, double
         q += 1;
     double x = q * gs;
     const double lim = (p + radius < fov - 1) ? p + radius : fov - 1; /* min(size - 1, pos + radius) */
-    unsigned m = 0;
+    unsigned long long m = 0;
     while (x <= lim) {
         double k = rint(x * inv);
         int col = (int)k;
@@ -86,7 +87,7 @@ DEV unsigned axis_buckets(double p, double radius, double fov, double gs, double
                 if (rho > thr) col -= 1;
             }
         }
-        m |= 1u << col;
+        m |= 1ull << col;
         x += gs;
     }
     return m;
@@ -151,14 +152,14 @@ DEV void axis_buckets2_bits(double p, double radius, double fov, double gs, doub
 template <class F>
 DEV void for_each_fov_bucket(double ox, double oy, double radius, double left, double top, double fov, double gs,
                              double inv, int cols, bool canon, F f) {
-    unsigned mx = axis_buckets(ox - left, radius, fov, gs, inv, canon);
-    const unsigned my = axis_buckets(oy - top, radius, fov, gs, inv, canon);
+    unsigned long long mx = axis_buckets(ox - left, radius, fov, gs, inv, canon);
+    const unsigned long long my = axis_buckets(oy - top, radius, fov, gs, inv, canon);
     while (mx) {
-        int col = __ffs(mx) - 1;
+        int col = __ffsll((long long)mx) - 1;
         mx &= mx - 1;
-        unsigned t = my;
+        unsigned long long t = my;
         while (t) {
-            int row = __ffs(t) - 1;
+            int row = __ffsll((long long)t) - 1;
             t &= t - 1;
             f(col + row * cols);
         }

@@ -17,7 +17,8 @@ _lib = None
 EXPORTS = ["agar_layout_for_config", "agar_create", "agar_destroy", "agar_last_error", "agar_get_layout", "agar_num_envs",
            "agar_reset", "agar_reset_bots", "agar_observe", "agar_step", "agar_step_observe", "agar_get",
            "agar_debug_dump", "agar_debug_load", "agar_launch_count", "agar_step_host", "agar_rollout_random",
-           "agar_set_tile_width", "agar_get_tile_width", "agar_state_ptr"]
+           "agar_set_tile_width", "agar_get_tile_width", "agar_state_ptr",
+           "agar_step_host_begin", "agar_step_host_end"]
 
 
 def load_library():
@@ -48,6 +49,8 @@ def load_library():
     lib.agar_launch_count.argtypes = [vp]
     lib.agar_launch_count.restype = ctypes.c_int64
     lib.agar_step_host.argtypes = [vp, vp, i32, vp, vp, vp, vp]
+    lib.agar_step_host_begin.argtypes = [vp, vp, i32, vp, vp]
+    lib.agar_step_host_end.argtypes = [vp, vp, vp, vp]
     lib.agar_rollout_random.argtypes = [vp, i32, i32, u32, vp, vp]
     lib.agar_set_tile_width.argtypes = [vp, i32]
     lib.agar_get_tile_width.argtypes = [vp]
@@ -189,6 +192,17 @@ class AgarBatch(object):
         a = np.ascontiguousarray(actions_np, dtype=np.float32)
         self._check(self.lib.agar_step_host(self.h, a.ctypes.data, int(n_frames), obs_out.ctypes.data,
                                             reward_out.ctypes.data, done_out.ctypes.data, self._stream()))
+
+    def step_host_begin(self, actions_np, n_frames, obs_out):
+        """First half of step_host: enqueue on torch's current stream and return (buffers must stay alive and unchanged
+        until step_host_end)."""
+        a = np.ascontiguousarray(actions_np, dtype=np.float32)
+        self._pending = (a, obs_out)
+        self._check(self.lib.agar_step_host_begin(self.h, a.ctypes.data, int(n_frames), obs_out.ctypes.data, self._stream()))
+
+    def step_host_end(self, reward_out, done_out):
+        self._check(self.lib.agar_step_host_end(self.h, reward_out.ctypes.data, done_out.ctypes.data, self._stream()))
+        self._pending = None
 
     # ---- parity / debugging
     def dump(self, env_index):

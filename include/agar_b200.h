@@ -292,6 +292,12 @@ int64_t agar_launch_count(const AgarEnv* env);
  * Buffers should be pinned for full PCIe speed.  Synchronises `stream` before returning. */
 int agar_step_host(AgarEnv* env, const float* actions_host, int n_frames, float* obs_host, float* reward_host,
                    uint8_t* done_host, void* stream);
+/* The same call in two halves, so that a caller can keep several groups of envs (one handle + one stream each) in
+ * flight: _begin enqueues H2D + frames + observe + D2H and returns at once; _end waits for that group and fills
+ * reward / done.  obs_host and actions_host must stay valid (and should be pinned) until _end returns.
+ * agar_step_host == _begin followed by _end. */
+int agar_step_host_begin(AgarEnv* env, const float* actions_host, int n_frames, float* obs_host, void* stream);
+int agar_step_host_end(AgarEnv* env, float* reward_host, uint8_t* done_host, void* stream);
 
 #ifdef __cplusplus
 }

@@ -830,12 +830,13 @@ static int in_fov(double x, double y, double r, double fx, double fy, double fov
 }
 
 /* ------------------------------------------------------------------ grid vision (bot.py:326-497, spatialHashTable.py:85-112) */
+#define AGAR_GRID_NB (65 * 65) /* (G + 1)^2 buckets, G <= 63 (agar_layout.h) */
 typedef struct GridTables {
     int cols, canonical;
-    double pel_sum[1100];
-    double own_max[1100], enemy_max[1100], vir_best_r[1100], vir_mass[1100];
-    uint8_t pel_has[1100], own_has[1100], enemy_has[1100], vir_has[1100];
-    int stamp[1100];
+    double pel_sum[AGAR_GRID_NB];
+    double own_max[AGAR_GRID_NB], enemy_max[AGAR_GRID_NB], vir_best_r[AGAR_GRID_NB], vir_mass[AGAR_GRID_NB];
+    uint8_t pel_has[AGAR_GRID_NB], own_has[AGAR_GRID_NB], enemy_has[AGAR_GRID_NB], vir_has[AGAR_GRID_NB];
+    int stamp[AGAR_GRID_NB];
     int serial;
 } GridTables;
 enum { T_PELLET, T_OWN, T_ENEMY, T_VIRUS };
@@ -907,7 +908,12 @@ static void observe_agent(OracleEnv* e, int k, int agent, float* obs, double* ob
     double left = fx - fov / 2, top = fy - fov / 2;
     double gs = fov / G;
     static __thread GridTables g;
-    memset(&g, 0, sizeof g);
+    {   /* clear what this observation can touch: (G + 1)^2 buckets */
+        size_t nb = (size_t)(G + 1) * (G + 1);
+        memset(g.pel_has, 0, nb), memset(g.own_has, 0, nb), memset(g.enemy_has, 0, nb), memset(g.vir_has, 0, nb);
+        memset(g.stamp, 0, nb * sizeof(int));
+        g.serial = 0;
+    }
     g.cols = cf->obs_mode == AGAR_OBS_CANONICAL ? G : (int)ceil(fov / gs); /* spatialHashTable.py:19 */
     g.canonical = cf->obs_mode == AGAR_OBS_CANONICAL;
     Rect ra = rect_of(e, fx, fy, fov / 2);
@@ -947,9 +953,9 @@ static void observe_agent(OracleEnv* e, int k, int agent, float* obs, double* ob
                 continue;
             grid_insert(&g, T_VIRUS, o->x, o->y, o->radius, o->mass, left, top, fov, gs);
         }
-    static __thread double pel[1100], own[1100], enemy[1100], vir[1100], wall[1100];
-    memset(pel, 0, sizeof pel), memset(own, 0, sizeof own), memset(enemy, 0, sizeof enemy);
-    memset(vir, 0, sizeof vir), memset(wall, 0, sizeof wall);
+    static __thread double pel[AGAR_GRID_NB], own[AGAR_GRID_NB], enemy[AGAR_GRID_NB], vir[AGAR_GRID_NB], wall[AGAR_GRID_NB];
+    memset(pel, 0, GG * sizeof(double)), memset(own, 0, GG * sizeof(double)), memset(enemy, 0, GG * sizeof(double));
+    memset(vir, 0, GG * sizeof(double)), memset(wall, 0, GG * sizeof(double));
     double midx = left + gs / 2, midy = top + gs / 2;
     for (int c = 0; c < G; ++c) {
         for (int r = 0; r < G; ++r) {
@@ -970,7 +976,7 @@ static void observe_agent(OracleEnv* e, int k, int agent, float* obs, double* ob
         midy += gs;
     }
     /* channel order bot.py:458-495 */
-    static __thread double out[16 * 1024];
+    static __thread double out[11 * 63 * 63 + 16];
     int n = 0;
     float* hist = e->L.n_hist ? e->hist + (size_t)agent * e->L.n_hist * GG : NULL;
 #define EMIT(src)                                      \

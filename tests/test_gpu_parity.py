@@ -39,6 +39,10 @@ VARIATIONS = [
     (dict(overrides={"use_second_last_action": 1, "self_grid_slf": 1, "enemy_grid_slf": 1}, num_nn=1, num_greedy=1,
           virus=True, split=True, eject=True), 32),
     (dict(overrides={"use_totalmass": 0}), 8), (dict(overrides={"use_fovsize": 0}), 2), (dict(pellet_spawn=False), 8),
+    # large grids (the handcraft-CNN observation, G = 42; general kernel, 64-bit bucket masks), SURVEY §8f rank 3
+    (dict(grid=42, overrides={"use_fovsize": 0, "use_totalmass": 0}), None), (dict(grid=63), None), (dict(grid=20, obs_mode=1), None),
+    (dict(grid=42, num_nn=1, num_greedy=1, virus=True, split=True, eject=True), 32),
+    (dict(grid=42, num_nn=2, num_greedy=2, virus=True, split=True, eject=True, obs_mode=1), 32),
 ]
 
 
@@ -257,8 +261,12 @@ def test_error_behaviour(torch_cuda):
     bad = lay.derive_config(eject=True)  # eject without split: TypeError in the reference (bot.py:568)
     assert lib.agar_create(ctypes.byref(bad), 4, 0, 0, 0, None, ctypes.byref(h)) == -4
     assert b"rejected" in lib.agar_last_error(None)
-    cfg = lay.derive_config(grid=20)     # CNN-sized grids are a "next" row
-    assert lib.agar_create(ctypes.byref(cfg), 4, 0, 0, 0, None, ctypes.byref(h)) == -4
+    cfg = lay.derive_config(grid=64)     # bucket columns are a 64-bit mask: G <= 63 (CNN_INPUT_DIM_2 = 84 is not covered)
+    assert lib.agar_create(ctypes.byref(cfg), 4, 0, 0, 0, None, ctypes.byref(h)) == -1
+    cnn = AgarBatch(lay.derive_config(grid=42), 4)
+    with pytest.raises(AgarError):
+        cnn.set_tile_width(8)            # large grids run on the general kernel only
+    assert cnn.tile_width == 32
     assert lib.agar_create(ctypes.byref(lay.derive_config()), 4, 99, 0, 0, None, ctypes.byref(h)) == -2  # no such device
     b = AgarBatch(lay.derive_config(), 8)
     assert lib.agar_step(b.h, None, 1, None) == -1 and b"NULL" in lib.agar_last_error(b.h)
@@ -360,3 +368,24 @@ def test_batched_td_targets_equal_the_reference_loop(torch_cuda):
         assert abs(float(td[i]) - td_e) < 1e-5
     td2, loss = lrn.learn(s, a, r, s2, d, torch.ones(B, device="cuda"))
     assert np.isfinite(loss) and td2.shape == (B,)
+
+
+def test_step_host_in_two_halves(torch_cuda):
+    """agar_step_host_begin / _end == agar_step_host; _end without _begin is an error, not a hang."""
+    import torch
+    from aigar_b200.env import AgarBatch, AgarError
+    cfg = lay.derive_config()
+    a, b = AgarBatch(cfg, 64, seed=4), AgarBatch(cfg, 64, seed=4)
+    L = a.layout
+    out = [[np.zeros((64, 1, L.state_len), np.float32), np.zeros((64, 1), np.float32), np.zeros((64, 1), np.uint8)] for _ in range(2)]
+    rng = np.random.default_rng(0)
+    with pytest.raises(AgarError):
+        b.step_host_end(out[1][1], out[1][2])
+    for t in range(12):
+        act = rng.random((64, 1, 4)).astype(np.float32)
+        a.step_host(act, 8, *out[0])
+        b.step_host_begin(act, 8, out[1][0])
+        b.step_host_end(out[1][1], out[1][2])
+        for x, y in zip(out[0], out[1]):
+            assert np.array_equal(x, y)
+    assert torch.equal(a.state_tensor(), b.state_tensor())

@@ -54,6 +54,9 @@ VARIATIONS = [
     dict(num_nn=3, num_greedy=1, split=True, eject=True, obs_mode=1),
     dict(overrides={"use_second_last_action": 1, "self_grid_slf": 1, "enemy_grid_slf": 1}, num_nn=1, num_greedy=1,
          virus=True, split=True, eject=True),
+    dict(grid=42, overrides={"use_fovsize": 0, "use_totalmass": 0}),   # the handcraft-CNN grid (bot.py:103-111), §8f rank 3
+    dict(grid=42, num_nn=1, num_greedy=1, virus=True, split=True, eject=True),
+    dict(grid=63),
 ]
 
 

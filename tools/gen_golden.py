@@ -19,6 +19,10 @@ CASES = {
     # obs_mode = AGAR_OBS_CANONICAL: the FOV grid always has G columns (the harness patches spatialHashTable.__init__)
     "cfg1_pellet_canonical": (dict(obs_mode=1), 640, 3, 17, 80),
     "cfg3_1v1_canonical": (dict(num_nn=1, num_greedy=1, virus=True, split=True, eject=True, obs_mode=1), 480, 5, 2, 60),
+    # the "handcraft CNN" observation = the same grid encoder at G = CNN_INPUT_DIM_1 = 42, no extras
+    # (src/model/bot.py:103-111,276-282; networkParameters.py:195-208)
+    "cnn42_pellet_canonical": (dict(grid=42, obs_mode=1, overrides={"use_fovsize": 0, "use_totalmass": 0}), 320, 11, 3, 80),
+    "cnn42_1v1": (dict(grid=42, num_nn=1, num_greedy=1, virus=True, split=True, eject=True), 160, 13, 1, 40),
 }
 
 
