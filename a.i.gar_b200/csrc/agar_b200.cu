@@ -83,8 +83,14 @@ __device__ __forceinline__ void bind_ctx(Ctx<W>& c, const DevParams& P, int tile
 }
 
 /* ------------------------------------------------------------------ the step kernel */
-template <int W, bool FULL>
-__global__ void __launch_bounds__(512)
+template <int W, bool FULL, int MAXT>
+/* minBlocks = 1 matters for the multi-agent kernels: with maxThreads alone ptxas budgets for two 512-thread CTAs per SM
+ * (64 registers, 540 bytes of spills); one CTA per SM is what their shared memory allows anyway -> 112-116 registers, no
+ * spills (measured +11 % config 3, +7 % config 4).  The single-cell general kernel runs many small CTAs per SM and keeps
+ * the 64-register budget (measured -13 % at 65536 envs with 125 registers).  MAXT = 1024: 32 envs per CTA when their hot
+ * sections fit (1-vs-greedy config): twice the warps walking the frame body in lock-step is worth more (+26 %) than the
+ * registers (64, with spills). */
+__global__ void __launch_bounds__(MAXT, (FULL || MAXT > 512) ? 1 : 2)
 k_main(const __grid_constant__ DevParams P, uint8_t* __restrict__ state, const float* __restrict__ actions,
        float* __restrict__ obs, int n_frames, int n_dec, int flags, uint32_t dec_base) {
     const int tiles = blockDim.x / W;
@@ -256,7 +262,7 @@ k_simple(const __grid_constant__ DevParams P, const SimplePlan SP, uint8_t* __re
 /* mode 0: Model(...) + createBot*K + Model.initialize (model.py:51,154-162,90-94; field.py:57-67)
  * mode 1: Model.resetModel -> Field.reset (field.py:69-83)      mode 2: Model.resetBots (bot.py:125-164) */
 template <int W, bool FULL>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(1024)
 k_init(const __grid_constant__ DevParams P, uint8_t* __restrict__ state, const uint8_t* __restrict__ mask, int mode) {
     const int tiles = blockDim.x / W;
     const int env0 = blockIdx.x * tiles;
@@ -416,9 +422,10 @@ static bool plan_launch(AgarEnv* e, int W) {
     const size_t budget = 200 * 1024;
     size_t per_tile = (e->P.stage == 1 ? (size_t)e->P.rec_stride : 0) + (size_t)e->P.scratch_bytes +
                       (e->P.stage >= 2 ? (size_t)((e->P.hot_a + 15) / 16 * 16) + (size_t)((e->L.pellet_cap * 4 + 15) / 16 * 16) : 0);
-    int tiles = e->full ? 512 / W : 128 / W; /* as many envs per CTA as fit: the barriers then align more warps */
+    const int max_threads = (e->full && W == 32) ? 1024 : 512; /* k_main<32, true, 1024> exists for 32-lane tiles only */
+    int tiles = e->full ? max_threads / W : 128 / W; /* as many envs per CTA as fit: the barriers then align more warps */
     if (getenv("AGAR_MAX_TILES")) tiles = atoi(getenv("AGAR_MAX_TILES"));
-    if (tiles * W > 512) tiles = 512 / W;
+    if (tiles * W > max_threads) tiles = max_threads / W;
     while (tiles > 1 && per_tile * tiles > budget) tiles -= 1;
     if (W == 32 && tiles > 4) tiles -= tiles % 4; /* warps spread evenly over the four schedulers of an SM */
     if (per_tile * tiles > budget) return false;
@@ -429,18 +436,25 @@ static bool plan_launch(AgarEnv* e, int W) {
     return true;
 }
 
+template <int W, bool FULL, int MAXT>
+static cudaError_t launch_main_k(AgarEnv* e, const float* actions, float* obs, int n_frames, int n_dec, int flags,
+                                 uint32_t dec_base, cudaStream_t s) {
+    cudaError_t err = cudaSuccess;
+    const long long key = (long long)W * (1ll << 32) + (long long)e->smem_bytes + ((long long)MAXT << 40);
+    if (e->attr_main != key) { /* once per launch shape, not per launch */
+        err = cudaFuncSetAttribute(k_main<W, FULL, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes);
+        if (err != cudaSuccess) return err;
+        e->attr_main = key;
+    }
+    int blocks = (e->n_envs + e->tiles - 1) / e->tiles;
+    k_main<W, FULL, MAXT><<<blocks, e->threads, e->smem_bytes, s>>>(e->P, e->state, actions, obs, n_frames, n_dec, flags, dec_base);
+    return cudaGetLastError();
+}
 template <int W, bool FULL>
 static cudaError_t launch_main_t(AgarEnv* e, const float* actions, float* obs, int n_frames, int n_dec, int flags,
                                  uint32_t dec_base, cudaStream_t s) {
-    cudaError_t err = cudaSuccess;
-    if (e->attr_main != (long long)W * (1ll << 32) + (long long)e->smem_bytes) { /* once per launch shape, not per launch */
-        err = cudaFuncSetAttribute(k_main<W, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes);
-        if (err != cudaSuccess) return err;
-        e->attr_main = (long long)W * (1ll << 32) + (long long)e->smem_bytes;
-    }
-    int blocks = (e->n_envs + e->tiles - 1) / e->tiles;
-    k_main<W, FULL><<<blocks, e->threads, e->smem_bytes, s>>>(e->P, e->state, actions, obs, n_frames, n_dec, flags, dec_base);
-    return cudaGetLastError();
+    if (W == 32 && FULL && e->threads > 512) return launch_main_k<32, true, 1024>(e, actions, obs, n_frames, n_dec, flags, dec_base, s);
+    return launch_main_k<W, FULL, 512>(e, actions, obs, n_frames, n_dec, flags, dec_base, s);
 }
 template <int W, bool FULL>
 static cudaError_t launch_init_t(AgarEnv* e, const uint8_t* mask, int mode, cudaStream_t s) {

@@ -6,20 +6,19 @@
 #pragma once
 #include "agar_dev.cuh"
 
-/* scratch layout used while observing (aliases the velocity scratch of update_players) */
+/* scratch layout used while observing (aliases the velocity scratch of update_players).  The multi-agent encoder
+ * builds its channels ONE AT A TIME through a single 8-byte table, so an env needs (G+1)^2 * 12 bytes of table scratch
+ * instead of (G+1)^2 * 44: 32 envs of the 1-vs-greedy config then share a CTA (measured +26 %). */
 struct ObsScratch {
-    int* pel_i;       /* [(G+1)^2] integer pellet mass per FOV bucket              */
+    int* pel_i;       /* [(G+1)^2] integer pellet mass per FOV bucket; later: 1 + index of the bucket's virus */
     double* mid;      /* [2][G]    gsMidPoint sequences (x then y)                 */
-    double* dsum;     /* FULL: pellet sums incl. float pellets                     */
-    double* own;      /* FULL: biggest own cell mass per bucket (as u64 bit patterns while accumulating) */
-    double* enemy;    /* FULL */
-    double* vir_r;    /* FULL: best virus radius per bucket                        */
-    double* vir_m;    /* FULL: its mass                                            */
+    double* tab;      /* FULL: [(G+1)^2] the channel being built (pellet sums incl. float pellets, then biggest own /
+                       * enemy cell mass as u64 bit patterns, then the best virus radius) */
 };
 __host__ __device__ inline int obs_scratch_bytes(int G, bool full) {
     int nb = (G + 1) * (G + 1);
     int bytes = ((nb * 4 + 7) / 8) * 8 + 2 * G * 8;
-    if (full) bytes += 5 * nb * 8;
+    if (full) bytes += nb * 8;
     return bytes;
 }
 DEV ObsScratch obs_scratch(uint8_t* base, int G, bool full) {
@@ -29,14 +28,7 @@ DEV ObsScratch obs_scratch(uint8_t* base, int G, bool full) {
     base += ((nb * 4 + 7) / 8) * 8;
     s.mid = (double*)base;
     base += 2 * G * 8;
-    s.dsum = s.own = s.enemy = s.vir_r = s.vir_m = nullptr;
-    if (full) {
-        s.dsum = (double*)base;
-        s.own = s.dsum + nb;
-        s.enemy = s.own + nb;
-        s.vir_r = s.enemy + nb;
-        s.vir_m = s.vir_r + nb;
-    }
+    s.tab = full ? (double*)base : nullptr;
     return s;
 }
 
@@ -182,15 +174,8 @@ DEV void observe_agent(Ctx<W>& c, const DevParams& P, int k, int agent, float* o
     const int cols = canon ? G : (int)ceil(fov / gs); /* spatialHashTable.py:19 */
     const int nbk = cols * cols;
     ObsScratch sc = obs_scratch(c.scratch, G, FULL);
-    for (int i = c.lane; i < nbk; i += W) {
-        sc.pel_i[i] = 0;
-        if (FULL) {
-            ((unsigned long long*)sc.own)[i] = 0ull;
-            ((unsigned long long*)sc.enemy)[i] = 0ull;
-            sc.vir_r[i] = 0.0;
-            sc.vir_m[i] = 0.0;
-        }
-    }
+    unsigned long long* tabu = (unsigned long long*)sc.tab;
+    for (int i = c.lane; i < nbk; i += W) sc.pel_i[i] = 0;
     if (c.lane == 0) { /* gsMidPoint sequences: mid += gsSize, accumulated exactly like the reference loop */
         double mx = left + gs / 2, my = top + gs / 2;
         for (int i = 0; i < G; ++i) {
@@ -202,7 +187,26 @@ DEV void observe_agent(Ctx<W>& c, const DevParams& P, int k, int agent, float* o
     }
     c.t.sync();
     const Rect ra = rect_of(P.S, fx, fy, fov / 2);
-    /* integer pellets (field.getPelletsInFov -> insertAllFloatingPointObjects): integer adds commute */
+    /* channel slots in bot.py:458-495 order: PELLET, SELF, WALL, ENEMY, VIRUS, SELF_SLF, SELF_LF, ENEMY_SLF, ENEMY_LF */
+    int ch = 0;
+    const int ch_pel = cf.pellet_grid ? ch++ : -1;
+    const int ch_self = (FULL && cf.self_grid) ? ch++ : -1;
+    const int ch_wall = (FULL && cf.wall_grid) ? ch++ : -1;
+    const int ch_enemy = (FULL && cf.enemy_grid) ? ch++ : -1;
+    const int ch_virus = (FULL && cf.virus_grid) ? ch++ : -1;
+    const int ch_self_slf = (FULL && cf.self_grid_slf) ? ch++ : -1;
+    const int ch_self_lf = (FULL && cf.self_grid_lf) ? ch++ : -1;
+    const int ch_enemy_slf = (FULL && cf.enemy_grid_slf) ? ch++ : -1;
+    const int ch_enemy_lf = (FULL && cf.enemy_grid_lf) ? ch++ : -1;
+    float* hist = (FULL && P.L.n_hist) ? c.hist + (size_t)agent * P.L.n_hist * GG : nullptr;
+    /* square idx of the G x G view (bucket index uses G, not cols: the reference's shear when cols == G + 1): does it
+     * show anything?  squares entirely outside the field do not (bot.py:392-393) */
+    auto inside = [&](int idx) {
+        int cc = idx / G, r = idx - cc * G;
+        double midx = sc.mid[r], midy = sc.mid[G + cc];
+        return !(midx + gs / 2 < 0 || midx - gs / 2 > S || midy + gs / 2 < 0 || midy - gs / 2 > S);
+    };
+    /* ---- PELLET: integer pellets (field.getPelletsInFov -> insertAllFloatingPointObjects): integer adds commute */
     /* integer window that contains every pellet in_fov() can accept (radius < 1) */
     const int wx0 = (int)floor(fx - fov / 2) - 1, wx1 = (int)ceil(fx + fov / 2) + 1;
     const int wy0 = (int)floor(fy - fov / 2) - 1, wy1 = (int)ceil(fy + fov / 2) + 1;
@@ -216,116 +220,95 @@ DEV void observe_agent(Ctx<W>& c, const DevParams& P, int k, int agent, float* o
         for_each_fov_bucket((double)px, (double)py, pr, left, top, fov, gs, inv, cols, canon,
                             [&](int id) { atomicAdd(&sc.pel_i[id], pm); });
     }
-    if (FULL) {
-        /* player cells: max commutes; positive doubles order like their bit patterns */
-        const int K = P.L.n_players, cap = P.L.cell_cap;
-        for (int idx = c.lane; idx < K * cap; idx += W) {
-            int k2 = idx / cap, j = idx - k2 * cap;
-            if (j >= c.pl[k2].n_cells) continue;
-            const AgarCell* o = CELLP(c, P, k2, j);
-            if (k2 == k) { /* own cells: no hash lookup (bot.py:344) */
-                if (!in_fov(o->x, o->y, o->radius, fx, fy, fov)) continue;
-            } else { /* enemies come through the player hash table (field.py:437-439) */
-                if (!(o->flags & AGAR_CF_INHASH) || !rect_hit(ra, rect_of(P.S, o->x, o->y, o->radius)) ||
-                    !in_fov(o->x, o->y, o->radius, fx, fy, fov))
-                    continue;
-            }
-            unsigned long long* grid = (unsigned long long*)(k2 == k ? sc.own : sc.enemy);
-            unsigned long long bits = (unsigned long long)__double_as_longlong(o->mass);
-            for_each_fov_bucket(o->x, o->y, o->radius, left, top, fov, gs, inv, cols, canon,
-                                [&](int id) { atomicMax(&grid[id], bits); });
-        }
-    }
     c.t.sync();
-    if (FULL) {
-        for (int i = c.lane; i < nbk; i += W) sc.dsum[i] = (double)sc.pel_i[i];
+    if (!FULL) {
+        for (int idx = c.lane; idx < GG; idx += W)
+            if (obs && ch_pel >= 0) obs[ch_pel * GG + idx] = inside(idx) ? (float)(double)sc.pel_i[idx] : 0.f;
+    } else {
+        for (int i = c.lane; i < nbk; i += W) sc.tab[i] = (double)sc.pel_i[i];
         c.t.sync();
-        if (c.lane == 0) {
-            /* float pellets are added after the integer ones, in slot order (canonical candidate order) */
-            if (c.h->n_fat)
-                for (int s = 0; s < P.L.fat_cap; ++s) {
-                    const AgarFatPellet* f = &c.fat[s];
-                    if (f->mass == 0) continue;
-                    if (!rect_hit(ra, rect_of(P.S, f->x, f->y, f->radius)) || !in_fov(f->x, f->y, f->radius, fx, fy, fov))
-                        continue;
-                    double fm = f->mass;
-                    for_each_fov_bucket(f->x, f->y, f->radius, left, top, fov, gs, inv, cols, canon,
-                                        [&](int id) { sc.dsum[id] = sc.dsum[id] + fm; });
+        if (c.lane == 0 && c.h->n_fat) /* float pellets are added after the integer ones, in slot order (canonical candidate order) */
+            for (int s = 0; s < P.L.fat_cap; ++s) {
+                const AgarFatPellet* f = &c.fat[s];
+                if (f->mass == 0) continue;
+                if (!rect_hit(ra, rect_of(P.S, f->x, f->y, f->radius)) || !in_fov(f->x, f->y, f->radius, fx, fy, fov)) continue;
+                double fm = f->mass;
+                for_each_fov_bucket(f->x, f->y, f->radius, left, top, fov, gs, inv, cols, canon,
+                                    [&](int id) { sc.tab[id] = sc.tab[id] + fm; });
+            }
+        c.t.sync();
+        for (int idx = c.lane; idx < GG; idx += W) {
+            if (obs && ch_pel >= 0) obs[ch_pel * GG + idx] = inside(idx) ? (float)sc.tab[idx] : 0.f;
+            if (ch_wall >= 0) { /* bot.py:443-450 */
+                int cc = idx / G, r = idx - cc * G;
+                double midx = sc.mid[r], midy = sc.mid[G + cc];
+                double lb = py_minS(S, py_max0(midx - gs / 2)), tb = py_minS(S, py_max0(midy - gs / 2));
+                double rb = py_max0(py_minS(S, midx + gs / 2)), bb = py_max0(py_minS(S, midy + gs / 2));
+                double free_area = (rb - lb) * (bb - tb);
+                double w = agar_round_dec(1 - (free_area / (gs * gs)), 1e3);
+                if (obs) obs[ch_wall * GG + idx] = (float)w;
+            }
+        }
+        /* ---- SELF then ENEMY: biggest cell mass per square; max commutes and positive doubles order like their bit
+         * patterns.  Own cells need no hash lookup (bot.py:344), enemies come through the player table (field.py:437-439). */
+        const int K = P.L.n_players, cap = P.L.cell_cap;
+        for (int pass = 0; pass < 2; ++pass) {
+            const bool own = pass == 0;
+            const int ch_now = own ? ch_self : ch_enemy, ch_slf = own ? ch_self_slf : ch_enemy_slf,
+                      ch_lf = own ? ch_self_lf : ch_enemy_lf;
+            if (ch_now < 0 && ch_slf < 0 && ch_lf < 0) continue;
+            c.t.sync();
+            for (int i = c.lane; i < nbk; i += W) tabu[i] = 0ull;
+            c.t.sync();
+            for (int idx = c.lane; idx < K * cap; idx += W) {
+                int k2 = idx / cap, j = idx - k2 * cap;
+                if ((k2 == k) != own || j >= c.pl[k2].n_cells) continue;
+                const AgarCell* o = CELLP(c, P, k2, j);
+                if (own) {
+                    if (!in_fov(o->x, o->y, o->radius, fx, fy, fov)) continue;
+                } else if (!(o->flags & AGAR_CF_INHASH) || !rect_hit(ra, rect_of(P.S, o->x, o->y, o->radius)) ||
+                           !in_fov(o->x, o->y, o->radius, fx, fy, fov))
+                    continue;
+                unsigned long long bits = (unsigned long long)__double_as_longlong(o->mass);
+                for_each_fov_bucket(o->x, o->y, o->radius, left, top, fov, gs, inv, cols, canon,
+                                    [&](int id) { atomicMax(&tabu[id], bits); });
+            }
+            c.t.sync();
+            float* h_lf = hist ? hist + (own ? 0 : 2) * GG : nullptr;  /* last observation's grid */
+            float* h_slf = hist ? hist + (own ? 1 : 3) * GG : nullptr; /* the one before */
+            for (int idx = c.lane; idx < GG; idx += W) {
+                double v = inside(idx) ? sc.tab[idx] : 0.0; /* 0 bits == 0.0: empty square */
+                if (obs && ch_now >= 0) obs[ch_now * GG + idx] = (float)v;
+                if (ch_slf >= 0) {
+                    if (obs) obs[ch_slf * GG + idx] = h_slf[idx];
+                    h_slf[idx] = h_lf[idx];
                 }
-            if (cf.virus_enabled) /* mass of the first virus with the largest radius (bot.py:436-441) */
+                if (ch_lf >= 0) {
+                    if (obs) obs[ch_lf * GG + idx] = h_lf[idx];
+                    h_lf[idx] = (float)v;
+                }
+            }
+        }
+        /* ---- VIRUS: mass of the first virus with the largest radius (bot.py:436-441); pel_i now holds 1 + its index */
+        if (ch_virus >= 0) {
+            c.t.sync();
+            for (int i = c.lane; i < nbk; i += W) sc.tab[i] = 0.0, sc.pel_i[i] = 0;
+            c.t.sync();
+            if (c.lane == 0 && cf.virus_enabled)
                 for (int v = 0; v < c.h->n_viruses; ++v) {
                     const AgarMote* o = &c.vir[v];
                     if (!(o->aux & AGAR_CF_INHASH) || !rect_hit(ra, rect_of(P.S, o->x, o->y, o->radius)) ||
                         !in_fov(o->x, o->y, o->radius, fx, fy, fov))
                         continue;
-                    double orr = o->radius, om = o->mass;
+                    double orr = o->radius;
                     for_each_fov_bucket(o->x, o->y, o->radius, left, top, fov, gs, inv, cols, canon, [&](int id) {
-                        if (orr > sc.vir_r[id]) sc.vir_r[id] = orr, sc.vir_m[id] = om;
+                        if (orr > sc.tab[id]) sc.tab[id] = orr, sc.pel_i[id] = v + 1;
                     });
                 }
-        }
-        c.t.sync();
-    }
-    /* read the G x G squares (bucket index uses G, not cols: the reference's shear when cols == G + 1) */
-    float* hist = (FULL && P.L.n_hist) ? c.hist + (size_t)agent * P.L.n_hist * GG : nullptr;
-    for (int idx = c.lane; idx < GG; idx += W) {
-        int cc = idx / G, r = idx - cc * G;
-        double midx = sc.mid[r], midy = sc.mid[G + cc];
-        bool inside = !(midx + gs / 2 < 0 || midx - gs / 2 > S || midy + gs / 2 < 0 || midy - gs / 2 > S);
-        double v_pel = 0, v_own = 0, v_enemy = 0, v_vir = 0;
-        if (inside) {
-            v_pel = FULL ? sc.dsum[idx] : (double)sc.pel_i[idx];
-            if (FULL) {
-                v_own = sc.own[idx];     /* 0 bits == 0.0: empty bucket */
-                v_enemy = sc.enemy[idx];
-                v_vir = sc.vir_m[idx];
-            }
-        }
-        int ch = 0;
-        if (cf.pellet_grid) {
-            if (obs) obs[ch * GG + idx] = (float)v_pel;
-            ++ch;
-        }
-        if (FULL) {
-            if (cf.self_grid) {
-                if (obs) obs[ch * GG + idx] = (float)v_own;
-                ++ch;
-            }
-            if (cf.wall_grid) { /* bot.py:443-450 */
-                double lb = py_minS(S, py_max0(midx - gs / 2)), tb = py_minS(S, py_max0(midy - gs / 2));
-                double rb = py_max0(py_minS(S, midx + gs / 2)), bb = py_max0(py_minS(S, midy + gs / 2));
-                double free_area = (rb - lb) * (bb - tb);
-                double w = agar_round_dec(1 - (free_area / (gs * gs)), 1e3);
-                if (obs) obs[ch * GG + idx] = (float)w;
-                ++ch;
-            }
-            if (cf.enemy_grid) {
-                if (obs) obs[ch * GG + idx] = (float)v_enemy;
-                ++ch;
-            }
-            if (cf.virus_grid) {
-                if (obs) obs[ch * GG + idx] = (float)v_vir;
-                ++ch;
-            }
-            if (cf.self_grid_slf) {
-                if (obs) obs[ch * GG + idx] = hist[1 * GG + idx];
-                hist[1 * GG + idx] = hist[0 * GG + idx];
-                ++ch;
-            }
-            if (cf.self_grid_lf) {
-                if (obs) obs[ch * GG + idx] = hist[0 * GG + idx];
-                hist[0 * GG + idx] = (float)v_own;
-                ++ch;
-            }
-            if (cf.enemy_grid_slf) {
-                if (obs) obs[ch * GG + idx] = hist[3 * GG + idx];
-                hist[3 * GG + idx] = hist[2 * GG + idx];
-                ++ch;
-            }
-            if (cf.enemy_grid_lf) {
-                if (obs) obs[ch * GG + idx] = hist[2 * GG + idx];
-                hist[2 * GG + idx] = (float)v_enemy;
-                ++ch;
+            c.t.sync();
+            for (int idx = c.lane; idx < GG; idx += W) {
+                int vi = sc.pel_i[idx];
+                if (obs) obs[ch_virus * GG + idx] = (inside(idx) && vi) ? (float)c.vir[vi - 1].mass : 0.f;
             }
         }
     }
