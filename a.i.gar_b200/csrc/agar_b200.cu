@@ -584,8 +584,9 @@ extern "C" int agar_create(const AgarConfig* cfg, int n_envs, int device, uint64
     /* Where a record lives during a launch.  1: whole record staged in shared memory (single-cell general kernel).
      * Multi-agent configs keep the record in HBM / L2 and cache on chip what every scan and lane-0 step reads:
      * 3 = header + players + cells + viruses + pellet pool if at least 12 envs per CTA still fit, else 2 = the pellet
-     * pool only (the 16-player arena: 23 KB of cells).  Measured (profiles/r01_sweep.txt): config 3 6.3e7 / 7.3e7 /
-     * 7.7e7 env-steps/s for 1 / 2 / 3; config 4 0.75e6 (1, 3 warps per SM) / 3.3e6 (2) / 1.6e6 (3). */
+     * pool only (the 16-player arena: 23 KB of cells).  Measured when the policy was chosen (16 envs per CTA): config 3
+     * 6.3e7 / 7.3e7 / 7.7e7 env-steps/s for 1 / 2 / 3; config 4 0.75e6 (1, 3 warps per SM) / 3.3e6 (2) / 1.6e6 (3);
+     * with 32 envs per CTA (profiles/r01_sweep.txt) config 3 does 9.1e7 (2) / 9.6e7 (3). */
     if (!e->full)
         P.stage = 1;
     else {
