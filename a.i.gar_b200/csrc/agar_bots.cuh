@@ -158,6 +158,40 @@ DEV void for_each_fov_bucket(double ox, double oy, double radius, double left, d
     }
 }
 
+/* Pellet slots of this lane whose integer position lies in the window [wx0, wx1] x [wy0, wy1]: f(slot, packed).
+ * Two phases, so that the expensive per-candidate body runs with many lanes: a converged scan marks the candidates in a
+ * per-lane bit mask (few of a big pool are in view: ~6 % in the 16-player arena, where the one-phase loop ran its body
+ * with 1.5 lanes of 32), then every lane walks its own candidates.  No collectives inside f. */
+template <int W, class F>
+DEV void for_each_window_pellet(const Ctx<W>& c, const DevParams& P, int wx0, int wx1, int wy0, int wy1, F f) {
+    const int cap = P.L.pellet_cap;
+    /* worth it when the window filters: with most of the field in view (single-cell configs) one phase is cheaper */
+    const bool filters = (long long)(wx1 - wx0 + 1) * (wy1 - wy0 + 1) * 2 < (long long)P.S * P.S;
+    if (cap <= 64 * W && filters) {
+        unsigned long long cand = 0;
+        int j = 0;
+        for (int s = c.lane; s < cap; s += W, ++j) {
+            uint32_t pk = c.pel[s];
+            int px = AGAR_PELLET_X(pk), py = AGAR_PELLET_Y(pk);
+            bool in = px >= wx0 && px <= wx1 && py >= wy0 && py <= wy1 && pk != 0;
+            cand |= (unsigned long long)in << j;
+        }
+        while (cand) {
+            int jj = __ffsll((long long)cand) - 1;
+            cand &= cand - 1;
+            int s = c.lane + W * jj;
+            f(s, c.pel[s]);
+        }
+    } else {
+        for (int s = c.lane; s < cap; s += W) {
+            uint32_t pk = c.pel[s];
+            int px = AGAR_PELLET_X(pk), py = AGAR_PELLET_Y(pk);
+            if (px < wx0 || px > wx1 || py < wy0 || py > wy1 || !pk) continue;
+            f(s, pk);
+        }
+    }
+}
+
 /* cooperative; bot.py:326-497 + :302-323 + :272-299.  obs: this agent's row of the caller's buffer or nullptr. */
 template <int W, bool FULL>
 DEV void observe_agent(Ctx<W>& c, const DevParams& P, int k, int agent, float* obs) {
@@ -210,16 +244,13 @@ DEV void observe_agent(Ctx<W>& c, const DevParams& P, int k, int agent, float* o
     /* integer window that contains every pellet in_fov() can accept (radius < 1) */
     const int wx0 = (int)floor(fx - fov / 2) - 1, wx1 = (int)ceil(fx + fov / 2) + 1;
     const int wy0 = (int)floor(fy - fov / 2) - 1, wy1 = (int)ceil(fy + fov / 2) + 1;
-    for (int s = c.lane; s < P.L.pellet_cap; s += W) {
-        uint32_t pk = c.pel[s];
-        int px = AGAR_PELLET_X(pk), py = AGAR_PELLET_Y(pk);
-        if (px < wx0 || px > wx1 || py < wy0 || py > wy1 || !pk) continue;
-        int pm = AGAR_PELLET_M(pk);
+    for_each_window_pellet(c, P, wx0, wx1, wy0, wy1, [&](int, uint32_t pk) {
+        int px = AGAR_PELLET_X(pk), py = AGAR_PELLET_Y(pk), pm = AGAR_PELLET_M(pk);
         double pr = P.pellet_r[pm & 3];
-        if (!rect_hit(ra, pellet_rect(px, py)) || !in_fov((double)px, (double)py, pr, fx, fy, fov)) continue;
+        if (!rect_hit(ra, pellet_rect(px, py)) || !in_fov((double)px, (double)py, pr, fx, fy, fov)) return;
         for_each_fov_bucket((double)px, (double)py, pr, left, top, fov, gs, inv, cols, canon,
                             [&](int id) { atomicAdd(&sc.pel_i[id], pm); });
-    }
+    });
     c.t.sync();
     if (!FULL) {
         for (int idx = c.lane; idx < GG; idx += W)
@@ -468,15 +499,12 @@ DEV void scripted_turn(Ctx<W>& c, const DevParams& P, int k) {
         int ord0 = 0;
         const int wx0 = (int)floor(fx - fov / 2) - 1, wx1 = (int)ceil(fx + fov / 2) + 1;
         const int wy0 = (int)floor(fy - fov / 2) - 1, wy1 = (int)ceil(fy + fov / 2) + 1;
-        for (int s = c.lane; s < P.L.pellet_cap; s += W) {
-            uint32_t pk = c.pel[s];
-            int px = AGAR_PELLET_X(pk), py = AGAR_PELLET_Y(pk);
-            if (px < wx0 || px > wx1 || py < wy0 || py > wy1 || !pk) continue; /* integer FOV window first */
-            int pm = AGAR_PELLET_M(pk);
+        for_each_window_pellet(c, P, wx0, wx1, wy0, wy1, [&](int s, uint32_t pk) { /* integer FOV window first */
+            int px = AGAR_PELLET_X(pk), py = AGAR_PELLET_Y(pk), pm = AGAR_PELLET_M(pk);
             double pr = P.pellet_r[pm & 3];
-            if (!rect_hit(ra, pellet_rect(px, py)) || !in_fov((double)px, (double)py, pr, fx, fy, fov)) continue;
+            if (!rect_hit(ra, pellet_rect(px, py)) || !in_fov((double)px, (double)py, pr, fx, fy, fov)) return;
             consider((double)px, (double)py, (double)pm, ord0 + s);
-        }
+        });
         ord0 += P.L.pellet_cap;
         for (int s = c.lane; s < P.L.fat_cap; s += W) {
             const AgarFatPellet* f = &c.fat[s];
