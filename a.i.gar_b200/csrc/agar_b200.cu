@@ -429,6 +429,20 @@ static bool plan_launch(AgarEnv* e, int W) {
     while (tiles > 1 && per_tile * tiles > budget) tiles -= 1;
     if (W == 32 && tiles > 4) tiles -= tiles % 4; /* warps spread evenly over the four schedulers of an SM */
     if (per_tile * tiles > budget) return false;
+    if (e->full && W == 32 && tiles > 8 && !getenv("AGAR_MAX_TILES")) {
+        /* one CTA per SM and all CTAs take about as long: fewer envs per CTA can fill the last wave better.  Cost model
+         * waves x envs-per-CTA (measured, config 3 at 16384 envs: 32 -> 1.01e8, 28 -> 1.05e8, 24 -> 0.97e8, 20 -> 0.89e8) */
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device);
+        long long best_cost = -1;
+        int best = tiles;
+        for (int t = tiles; t >= 8 && t >= tiles - 4; t -= 4) { /* one step: smaller CTAs lose lock-step efficiency */
+            long long ctas = (e->n_envs + t - 1) / t, waves = (ctas + sms - 1) / sms;
+            long long cost = waves * t;
+            if (best_cost < 0 || cost < best_cost) best_cost = cost, best = t;
+        }
+        tiles = best;
+    }
     e->W = W;
     e->tiles = tiles;
     e->threads = tiles * W;
@@ -453,7 +467,8 @@ static cudaError_t launch_main_k(AgarEnv* e, const float* actions, float* obs, i
 template <int W, bool FULL>
 static cudaError_t launch_main_t(AgarEnv* e, const float* actions, float* obs, int n_frames, int n_dec, int flags,
                                  uint32_t dec_base, cudaStream_t s) {
-    if (W == 32 && FULL && e->threads > 512) return launch_main_k<32, true, 1024>(e, actions, obs, n_frames, n_dec, flags, dec_base, s);
+    if (W == 32 && FULL && e->threads > 768) return launch_main_k<32, true, 1024>(e, actions, obs, n_frames, n_dec, flags, dec_base, s);
+    if (W == 32 && FULL && e->threads > 512) return launch_main_k<32, true, 768>(e, actions, obs, n_frames, n_dec, flags, dec_base, s);
     return launch_main_k<W, FULL, 512>(e, actions, obs, n_frames, n_dec, flags, dec_base, s);
 }
 template <int W, bool FULL>
