@@ -329,6 +329,27 @@ def main():
             b0.close()
         except Exception as ex:
             extra["obs_every_frame"] = {"error": str(ex)[:200]}
+        # BASELINE configs[2] / [3] (parity-test cases, reported for reference): multi-agent kernels, 96-frame launches
+        for name, kw, En in (("config3_1v1_greedy_16384", dict(num_nn=1, num_greedy=1, virus=True, split=True, eject=True), 16384),
+                             ("config4_arena_8192", dict(num_nn=8, num_greedy=8, virus=True, split=True, eject=True), 8192)):
+            try:
+                cm = lay.derive_config(**kw)
+                bm = AgarBatch(cm, En, device=local, seed=2026, first_env_id=3 * 10 ** 6)
+                bm.rollout_random(12, PERIOD, decision_base=0)
+                ts = []
+                for i in range(2):
+                    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    s.record()
+                    bm.rollout_random(12, PERIOD, decision_base=(1 + i) * 12)
+                    e.record()
+                    torch.cuda.synchronize()
+                    ts.append(s.elapsed_time(e))
+                ms = sum(ts) / len(ts)
+                extra[name] = {"value": En * 12 * PERIOD / (ms * 1e-3), "unit": UNIT, "ms_per_launch": ms, "frames_per_launch": 12 * PERIOD,
+                               "players": int(bm.layout.n_players), "state_len": int(bm.layout.state_len), "tile_width": bm.tile_width}
+                bm.close()
+            except Exception as ex:
+                extra[name] = {"error": str(ex)[:200]}
         try:  # BASELINE configs[4] shard: obs -> DLPack -> torch DQN forward -> arg-max -> 5x5 table -> 8 frames
             from aigar_b200.dqn import DQNDriver
             E3, ticks = 65536, 20
