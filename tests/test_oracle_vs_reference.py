@@ -67,3 +67,35 @@ def test_config_variations_equal_reference(kw):
     import compare_oracle_ref as cmp
     frames = 160 if kw.get("num_nn", 1) + kw.get("num_greedy", 0) + kw.get("num_random", 0) <= 2 else 90
     assert cmp.run(kw, frames, seed=31, verbose=False)
+
+
+def test_views_show_what_the_reference_objects_show():
+    """a.i.gar_b200/views.py: the getters the reference's View reads, over an env record, against
+    the live reference objects after 150 frames of the 1-vs-greedy config."""
+    import numpy as np
+    import aigar_b200.layout as lay
+    from aigar_b200.views import FieldView
+    from oracle import oracle as orc
+    cfg = lay.derive_config(num_nn=1, num_greedy=1, virus=True, split=True, eject=True)
+    ref, ora = rh.RefEnv(cfg, seed=9, env_id=2), orc.OracleEnv(cfg, seed=9, env_id=2)
+    rng = np.random.default_rng(1)
+    for t in range(150):
+        a = rng.random((1, 4)).astype(np.float32)
+        ref.step(a)
+        ora.frame(a)
+    fv, f = FieldView(ora.record), ref.field
+    assert fv.getWidth() == f.getWidth() and fv.getHeight() == f.getHeight()
+    key = lambda c: (round(c.getX(), 9), round(c.getY(), 9), round(c.getMass(), 9))
+    for mine, theirs in ((fv.getPellets(), f.getPellets()), (fv.getViruses(), f.getViruses()), (fv.getBlobs(), f.getBlobs()),
+                         (fv.getPlayerCells(), f.getPlayerCells())):
+        assert sorted(map(key, mine)) == sorted(map(key, theirs))
+        assert sorted(round(c.getRadius(), 9) for c in mine) == sorted(round(c.getRadius(), 9) for c in theirs)
+    for pv, p in zip(fv.getPlayers(), f.getPlayers()):
+        assert pv.getIsAlive() == p.getIsAlive() and len(pv.getCells()) == len(p.getCells())
+        assert abs(pv.getTotalMass() - p.getTotalMass()) < 1e-9
+        for cv, c in zip(pv.getCells(), p.getCells()):
+            assert cv.getPos() == list(c.getPos()) and cv.getMass() == c.getMass() and cv.getRadius() == c.getRadius()
+    p0 = f.getPlayers()[0]
+    if p0.getIsAlive():
+        pos, size = p0.getFovPos(), p0.getFovSize()
+        assert sorted(map(key, fv.getPelletsInFov(pos, size))) == sorted(map(key, f.getPelletsInFov(pos, size)))
