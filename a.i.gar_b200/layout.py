@@ -146,6 +146,8 @@ def layout_for_config(c):
     """Pure-Python twin of agar_layout_compute() (include/agar_layout.h); tests check they agree."""
     L = AgarLayout()
     k = c.n_players
+    if (c.enable_eject and not c.enable_split) or c.enable_greedy_split or (c.virus_grid and not c.virus_enabled):
+        raise ValueError("config rejected (agar_layout_compute: eject without split, greedy split, or a virus grid without viruses)")
     s = int(75.0 * math.sqrt(k))
     L.field_size, L.n_players = s, k
     L.n_agents = sum(1 for i in range(k) if c.bot_type[i] == BOT_NN)

@@ -22,6 +22,9 @@ static inline int agar_layout_compute(const AgarConfig* c, AgarLayout* L) {
     if (c->frame_skip < 0) return AGAR_E_INVALID;
     if (c->enable_greedy_split) return AGAR_E_UNSUPPORTED;
     if (c->enable_eject && !c->enable_split) return AGAR_E_UNSUPPORTED; /* reference raises TypeError, bot.py:568 */
+    /* VIRUS_GRID without VIRUS_SPAWN: the reference assigns gsVirus = None into the grid, a channel of NaN
+     * (bot.py:380-382, 481); networkParameters.py derives VIRUS_GRID from VIRUS_SPAWN, so only a hand-edited file gets here */
+    if (c->virus_grid && !c->virus_enabled) return AGAR_E_UNSUPPORTED;
     int n_agents = 0;
     for (int k = 0; k < K; ++k) {
         int t = c->bot_type[k];

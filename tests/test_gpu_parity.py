@@ -261,6 +261,8 @@ def test_error_behaviour(torch_cuda):
     bad = lay.derive_config(eject=True)  # eject without split: TypeError in the reference (bot.py:568)
     assert lib.agar_create(ctypes.byref(bad), 4, 0, 0, 0, None, ctypes.byref(h)) == -4
     assert b"rejected" in lib.agar_last_error(None)
+    nan_cfg = lay.derive_config(overrides={"virus_grid": 1})   # the reference would emit a NaN channel (bot.py:380-382)
+    assert lib.agar_create(ctypes.byref(nan_cfg), 4, 0, 0, 0, None, ctypes.byref(h)) == -4
     cfg = lay.derive_config(grid=64)     # bucket columns are a 64-bit mask: G <= 63 (CNN_INPUT_DIM_2 = 84 is not covered)
     assert lib.agar_create(ctypes.byref(cfg), 4, 0, 0, 0, None, ctypes.byref(h)) == -1
     cnn = AgarBatch(lay.derive_config(grid=42), 4)

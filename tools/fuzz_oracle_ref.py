@@ -20,8 +20,15 @@ for case in range(N):
               grid=rnd.choice([3, 5, 8, 11, 11, 14, 16, 19, 25]), frame_skip=rnd.choice([0, 1, 3, 7, 7, 9]),
               obs_mode=rnd.choice([0, 0, 1]), mass_as_reward=rnd.random() < 0.2,
               overrides={f: int(rnd.random() < 0.5) for f in rnd.sample(FLAGS, rnd.randint(0, 6))})
-    for _ in range(4):  # keep the stream aligned with tools/gpu_fuzz.py (tile, n_envs, frames, seed draws)
-        pass
+    try:
+        import aigar_b200.layout as lay
+        lay.layout_for_config(lay.derive_config(**kw))
+    except ValueError as ex:
+        print("case %d rejected by layout (%s)" % (case, ex))
+        continue
+    if kw["frame_skip"] == 0 and n_rd:
+        print("case %d skipped: the reference divides by zero (bot.py:244)" % case)
+        continue
     try:
         ok = cmp.run(kw, 60 if n_nn + n_gr + n_rd > 3 else 100, seed=rnd.randint(0, 999), verbose=False)
     except Exception:
