@@ -391,3 +391,14 @@ def test_step_host_in_two_halves(torch_cuda):
         for x, y in zip(out[0], out[1]):
             assert np.array_equal(x, y)
     assert torch.equal(a.state_tensor(), b.state_tensor())
+
+
+def test_random_configs_gpu_equals_oracle(torch_cuda):
+    """tools/gpu_fuzz.py: random flag / bot-mix / grid / frame-skip / tile-width combinations, CUDA vs the portable oracle."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "gpu_fuzz.py"), "10", "31"], capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 0 and "all OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

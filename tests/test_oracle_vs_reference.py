@@ -99,3 +99,14 @@ def test_views_show_what_the_reference_objects_show():
     if p0.getIsAlive():
         pos, size = p0.getFovPos(), p0.getFovSize()
         assert sorted(map(key, fv.getPelletsInFov(pos, size))) == sorted(map(key, f.getPelletsInFov(pos, size)))
+
+
+def test_random_configs_equal_reference():
+    """tools/fuzz_oracle_ref.py: random flag / bot-mix / grid / frame-skip combinations, oracle vs the executed reference."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_oracle_ref.py"), "6", "23"], capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

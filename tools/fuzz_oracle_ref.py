@@ -37,3 +37,4 @@ for case in range(N):
     print("case %d %s: %r" % (case, "OK" if ok else "FAILED", kw), flush=True)
     bad += 0 if ok else 1
 print("%d cases, %d failed" % (N, bad))
+sys.exit(1 if bad else 0)
