@@ -334,6 +334,21 @@ k_init(const __grid_constant__ DevParams P, uint8_t* __restrict__ state, const u
     }
 }
 
+/* agar_step_host with pinned (device-visible) caller buffers: observations and the packed reward | done words leave
+ * through the SMs' own stores over PCIe, so no copy-engine operation (and none of its start latency) sits between the
+ * step kernel and the host.  n16 / n4: 16-byte and trailing 4-byte units of the observation block. */
+__global__ void k_export(const uint4* __restrict__ obs, uint4* __restrict__ obs_host, size_t n16, size_t n4_tail,
+                         const uint32_t* __restrict__ turn, uint32_t* __restrict__ turn_host, size_t n4_turn) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x, i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (obs_host) {
+        for (size_t i = i0; i < n16; i += stride) obs_host[i] = obs[i];
+        const uint32_t* t = (const uint32_t*)(obs + n16);
+        uint32_t* th = (uint32_t*)(obs_host + n16);
+        for (size_t i = i0; i < n4_tail; i += stride) th[i] = t[i];
+    }
+    for (size_t i = i0; i < n4_turn; i += stride) turn_host[i] = turn[i];
+}
+
 /* agar_get: one thread per (env, agent) or per env, straight from HBM */
 __global__ void k_get(const __grid_constant__ DevParams P, const uint8_t* __restrict__ state, int which, void* out) {
     const int A = P.L.n_agents;
@@ -390,6 +405,7 @@ struct AgarEnv {
     uint8_t* d_done;
     void* h_turn; /* pinned */
     int host_pending; /* agar_step_host_begin issued, _end not yet */
+    int host_zerocopy; /* pinned caller buffers are read / written in place (AGAR_HOST_ZEROCOPY=0 disables) */
     long long attr_main, attr_simple; /* launch shapes whose max-dynamic-shared-memory attribute is already set */
 };
 static char g_create_err[256] = "";
@@ -742,28 +758,59 @@ extern "C" int agar_debug_load(AgarEnv* e, int env_index, const void* record_hos
     CU(cudaStreamSynchronize((cudaStream_t)stream));
     return AGAR_OK;
 }
+/* device-visible address of a pinned host buffer, or nullptr for pageable memory */
+static void* pinned_dev_ptr(const void* p) {
+    if (!p) return nullptr;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+}
+
 extern "C" int agar_step_host_begin(AgarEnv* e, const float* actions_host, int n_frames, float* obs_host, void* stream) {
     AgarEnv* env = e;
     if (!e || !actions_host || n_frames < 0) return AGAR_E_INVALID;
     CU(cudaSetDevice(e->device));
     cudaStream_t s = (cudaStream_t)stream;
     const size_t EA = (size_t)e->n_envs * (e->L.n_agents ? e->L.n_agents : 1);
+    const size_t turn_words = (EA * 5 + 3) / 4;
     if (!e->d_actions) {
         CU(cudaMalloc(&e->d_actions, EA * 4 * sizeof(float)));
         CU(cudaMalloc(&e->d_obs, EA * e->L.state_len * sizeof(float)));
-        CU(cudaMalloc(&e->d_reward, EA * 5)); /* packed: float reward[EA] | uint8 done[EA] -> one copy back */
-        CU(cudaMallocHost(&e->h_turn, EA * 5));
+        CU(cudaMalloc(&e->d_reward, turn_words * 4)); /* packed: float reward[EA] | uint8 done[EA] -> one copy back */
+        CU(cudaMallocHost(&e->h_turn, turn_words * 4));
         e->d_done = (uint8_t*)e->d_reward + EA * 4;
         CU(cudaMemsetAsync(e->d_obs, 0, EA * e->L.state_len * sizeof(float), s));
-        CU(cudaMemsetAsync(e->d_reward, 0, EA * 5, s));
+        CU(cudaMemsetAsync(e->d_reward, 0, turn_words * 4, s));
+        const char* zc = getenv("AGAR_HOST_ZEROCOPY");
+        e->host_zerocopy = zc ? atoi(zc) : 1;
     }
-    CU(cudaMemcpyAsync(e->d_actions, actions_host, EA * 4 * sizeof(float), cudaMemcpyHostToDevice, s));
+    /* Pinned caller buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory) are visible to the device: the step
+     * kernel reads the actions in place and k_export stores the results straight into them.  Pageable buffers take the
+     * copy-engine path. */
+    const float* act_dev = e->host_zerocopy ? (const float*)pinned_dev_ptr(actions_host) : nullptr;
+    float* obs_dev_host = (e->host_zerocopy && obs_host) ? (float*)pinned_dev_ptr(obs_host) : nullptr;
+    const bool zero_copy = act_dev && (!obs_host || (obs_dev_host && ((uintptr_t)obs_dev_host & 15) == 0));
+    if (!zero_copy) CU(cudaMemcpyAsync(e->d_actions, actions_host, EA * 4 * sizeof(float), cudaMemcpyHostToDevice, s));
     e->P.turn_reward = e->d_reward, e->P.turn_done = e->d_done; /* reward / done written by the step kernel itself */
-    int rc = launch_main(e, e->d_actions, e->d_obs, n_frames, 1, KF_OBS_AFTER, 0, s);
+    int rc = launch_main(e, zero_copy ? act_dev : e->d_actions, e->d_obs, n_frames, 1, KF_OBS_AFTER, 0, s);
     e->P.turn_reward = nullptr, e->P.turn_done = nullptr;
     if (rc != AGAR_OK) return rc;
-    if (obs_host) CU(cudaMemcpyAsync(obs_host, e->d_obs, EA * e->L.state_len * sizeof(float), cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(e->h_turn, e->d_reward, EA * 5, cudaMemcpyDeviceToHost, s));
+    const size_t obs_bytes = EA * e->L.state_len * sizeof(float);
+    if (zero_copy) {
+        void* turn_dev_host = nullptr;
+        CU(cudaHostGetDevicePointer(&turn_dev_host, e->h_turn, 0));
+        k_export<<<296, 256, 0, s>>>((const uint4*)e->d_obs, (uint4*)obs_dev_host, obs_bytes / 16, (obs_bytes % 16) / 4,
+                                     (const uint32_t*)e->d_reward, (uint32_t*)turn_dev_host, turn_words);
+        cudaError_t err = cudaGetLastError();
+        if (err != cudaSuccess) return fail(e, AGAR_E_CUDA, "kernel launch failed: %s", cudaGetErrorString(err));
+        e->launches += 1;
+    } else {
+        if (obs_host) CU(cudaMemcpyAsync(obs_host, e->d_obs, obs_bytes, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(e->h_turn, e->d_reward, EA * 5, cudaMemcpyDeviceToHost, s));
+    }
     e->host_pending = 1;
     return AGAR_OK;
 }

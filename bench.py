@@ -271,7 +271,7 @@ def main():
         e2e = {"value": world * E * frames * e2e_steps / dt, "unit": UNIT,
                "h2d_bytes_per_step": int(decisions * acts[0].nbytes),
                "d2h_bytes_per_step": int(decisions * (obs_h.nbytes + rew_h.nbytes + done_h.nbytes)),
-               "steps": e2e_steps, "calls_per_step": decisions, "api": "agar_step_host (C ABI, pinned host buffers)"}
+               "steps": e2e_steps, "calls_per_step": decisions, "api": "agar_step_host (C ABI, pinned host buffers: actions read in place by the step kernel, obs/reward/done stored over PCIe by k_export)"}
 
     # ---- episode statistics: the one optional collective, outside the timed region
     stats = batch.get(lay.GET_STATS).sum(dim=(0, 1))

@@ -289,7 +289,8 @@ int64_t agar_launch_count(const AgarEnv* env);
 
 /* ---- host-buffer convenience path (the e2e call: host arrays in, host arrays out) ----
  * actions_host float[E][A][4] -> H2D, n_frames frames, observe, D2H of obs/reward/done.
- * Buffers should be pinned for full PCIe speed.  Synchronises `stream` before returning. */
+ * Buffers should be pinned for full PCIe speed: pinned (device-visible) actions_host / obs_host are read and written in
+ * place by the kernels, pageable ones go through staging copies.  Synchronises `stream` before returning. */
 int agar_step_host(AgarEnv* env, const float* actions_host, int n_frames, float* obs_host, float* reward_host,
                    uint8_t* done_host, void* stream);
 /* The same call in two halves, so that a caller can keep several groups of envs (one handle + one stream each) in

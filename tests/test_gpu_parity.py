@@ -402,3 +402,29 @@ def test_random_configs_gpu_equals_oracle(torch_cuda):
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "gpu_fuzz.py"), "10", "31"], capture_output=True, text=True,
                        timeout=900)
     assert r.returncode == 0 and "all OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_step_host_pinned_buffers_equal_pageable(torch_cuda):
+    """Pinned caller buffers take the zero-copy route of agar_step_host (kernel reads the actions in place, k_export stores
+    the results over PCIe); pageable buffers take the copy-engine route.  Same results, multi-agent config included."""
+    import torch
+    from aigar_b200.env import AgarBatch
+    for kw, n in ((dict(), 257), (dict(num_nn=2, num_greedy=1, virus=True, split=True, eject=True), 33)):
+        cfg = lay.derive_config(**kw)
+        a, b = AgarBatch(cfg, n, seed=6), AgarBatch(cfg, n, seed=6)
+        L = a.layout
+        A = max(L.n_agents, 1)
+        pin = [torch.zeros((n, A, L.state_len)).pin_memory(), torch.zeros((n, A)).pin_memory(),
+               torch.zeros((n, A), dtype=torch.uint8).pin_memory(), torch.zeros((n, A, 4)).pin_memory()]
+        pg = [np.zeros((n, A, L.state_len), np.float32), np.zeros((n, A), np.float32), np.zeros((n, A), np.uint8)]
+        rng = np.random.default_rng(2)
+        launches0 = a.launch_count
+        for t in range(10):
+            act = rng.random((n, A, 4)).astype(np.float32)
+            pin[3].numpy()[:] = act
+            a.step_host(pin[3].numpy(), 8, pin[0].numpy(), pin[1].numpy(), pin[2].numpy())
+            b.step_host(act, 8, *pg)
+            for x, y in zip(pin[:3], pg):
+                assert np.array_equal(x.numpy(), y)
+        assert a.launch_count - launches0 == 20          # step kernel + export kernel per call
+        assert torch.equal(a.state_tensor(), b.state_tensor())
