@@ -221,12 +221,13 @@ DEV void observe_agent(Ctx<W>& c, const DevParams& P, int k, int agent, float* o
     }
     c.t.sync();
     const Rect ra = rect_of(P.S, fx, fy, fov / 2);
-    /* channel slots in bot.py:458-495 order: PELLET, SELF, WALL, ENEMY, VIRUS, SELF_SLF, SELF_LF, ENEMY_SLF, ENEMY_LF */
+    /* channel slots in bot.py:458-495 order: PELLET, SELF, WALL, ENEMY, ALL_PLAYER, VIRUS, SELF_SLF, SELF_LF, ENEMY_SLF, ENEMY_LF */
     int ch = 0;
     const int ch_pel = cf.pellet_grid ? ch++ : -1;
     const int ch_self = (FULL && cf.self_grid) ? ch++ : -1;
     const int ch_wall = (FULL && cf.wall_grid) ? ch++ : -1;
     const int ch_enemy = (FULL && cf.enemy_grid) ? ch++ : -1;
+    const int ch_all = (FULL && cf.all_player_grid) ? ch++ : -1;
     const int ch_virus = (FULL && cf.virus_grid) ? ch++ : -1;
     const int ch_self_slf = (FULL && cf.self_grid_slf) ? ch++ : -1;
     const int ch_self_lf = (FULL && cf.self_grid_lf) ? ch++ : -1;
@@ -283,19 +284,19 @@ DEV void observe_agent(Ctx<W>& c, const DevParams& P, int k, int agent, float* o
         /* ---- SELF then ENEMY: biggest cell mass per square; max commutes and positive doubles order like their bit
          * patterns.  Own cells need no hash lookup (bot.py:344), enemies come through the player table (field.py:437-439). */
         const int K = P.L.n_players, cap = P.L.cell_cap;
-        for (int pass = 0; pass < 2; ++pass) {
-            const bool own = pass == 0;
-            const int ch_now = own ? ch_self : ch_enemy, ch_slf = own ? ch_self_slf : ch_enemy_slf,
-                      ch_lf = own ? ch_self_lf : ch_enemy_lf;
+        for (int pass = 0; pass < 3; ++pass) { /* 0: own cells, 1: enemy cells, 2: ALL_PLAYER_GRID (both, bot.py:348-351) */
+            const bool own = pass == 0, all = pass == 2;
+            const int ch_now = all ? ch_all : (own ? ch_self : ch_enemy), ch_slf = all ? -1 : (own ? ch_self_slf : ch_enemy_slf),
+                      ch_lf = all ? -1 : (own ? ch_self_lf : ch_enemy_lf);
             if (ch_now < 0 && ch_slf < 0 && ch_lf < 0) continue;
             c.t.sync();
             for (int i = c.lane; i < nbk; i += W) tabu[i] = 0ull;
             c.t.sync();
             for (int idx = c.lane; idx < K * cap; idx += W) {
                 int k2 = idx / cap, j = idx - k2 * cap;
-                if ((k2 == k) != own || j >= c.pl[k2].n_cells) continue;
+                if ((!all && (k2 == k) != own) || j >= c.pl[k2].n_cells) continue;
                 const AgarCell* o = CELLP(c, P, k2, j);
-                if (own) {
+                if (k2 == k) {
                     if (!in_fov(o->x, o->y, o->radius, fx, fy, fov)) continue;
                 } else if (!(o->flags & AGAR_CF_INHASH) || !rect_hit(ra, rect_of(P.S, o->x, o->y, o->radius)) ||
                            !in_fov(o->x, o->y, o->radius, fx, fy, fov))

@@ -42,7 +42,7 @@ class AgarConfig(ctypes.Structure):
         ("mass_as_reward", ctypes.c_int32), ("obs_mode", ctypes.c_int32),
         ("fat_cap", ctypes.c_int32), ("virus_cap", ctypes.c_int32), ("blob_cap", ctypes.c_int32),
         ("event_cap", ctypes.c_int32),
-        ("pellet_cap", ctypes.c_int32), ("reserved", ctypes.c_int32 * 6),
+        ("pellet_cap", ctypes.c_int32), ("all_player_grid", ctypes.c_int32), ("reserved", ctypes.c_int32 * 5),
         ("reward_scale", ctypes.c_double), ("reward_term", ctypes.c_double),
         ("death_term", ctypes.c_double), ("death_factor", ctypes.c_double),
     ]
@@ -146,8 +146,11 @@ def layout_for_config(c):
     """Pure-Python twin of agar_layout_compute() (include/agar_layout.h); tests check they agree."""
     L = AgarLayout()
     k = c.n_players
-    if (c.enable_eject and not c.enable_split) or c.enable_greedy_split or (c.virus_grid and not c.virus_enabled):
-        raise ValueError("config rejected (agar_layout_compute: eject without split, greedy split, or a virus grid without viruses)")
+    if (c.enable_eject and not c.enable_split) or c.enable_greedy_split or (c.virus_grid and not c.virus_enabled) or \
+            (c.all_player_grid and (c.self_grid or c.enemy_grid or c.self_grid_lf or c.self_grid_slf or c.enemy_grid_lf or
+                                    c.enemy_grid_slf)):
+        raise ValueError("config rejected (agar_layout_compute: eject without split, greedy split, a virus grid without viruses, "
+                         "or the all-player grid together with self / enemy grids)")
     s = int(75.0 * math.sqrt(k))
     L.field_size, L.n_players = s, k
     L.n_agents = sum(1 for i in range(k) if c.bot_type[i] == BOT_NN)
@@ -169,7 +172,7 @@ def layout_for_config(c):
     g = c.grid_squares
     L.grid_squares = g
     L.n_grids = sum(int(bool(x)) for x in (c.pellet_grid, c.self_grid, c.wall_grid, c.virus_grid, c.enemy_grid,
-                                           c.self_grid_lf, c.self_grid_slf, c.enemy_grid_lf, c.enemy_grid_slf))
+                                           c.self_grid_lf, c.self_grid_slf, c.enemy_grid_lf, c.enemy_grid_slf, c.all_player_grid))
     L.n_extra = (int(bool(c.use_fovsize)) + int(bool(c.use_totalmass)) + 4 * int(bool(c.use_last_action)) +
                  4 * int(bool(c.use_second_last_action)) + int(bool(c.use_last_fovsize)))
     L.state_len = g * g * L.n_grids + L.n_extra

@@ -72,7 +72,9 @@ typedef struct AgarConfig {
     int32_t blob_cap;                     /* ejected-blob pool   (0 = default)                       */
     int32_t event_cap;                    /* per-frame event log entries per env (0 = no log)        */
     int32_t pellet_cap;                   /* integer-pellet slots; 0 = default (the refill target, field.py:65) */
-    int32_t reserved[6];
+    int32_t all_player_grid;              /* ALL_PLAYER_GRID :88-91 — one channel with the biggest cell of ANY player per square,
+                                           * instead of the self / enemy channels (which must then be off)      */
+    int32_t reserved[5];
     double reward_scale;                  /* REWARD_SCALE :70 */
     double reward_term;                   /* REWARD_TERM  :69 */
     double death_term;                    /* DEATH_TERM   :71 */

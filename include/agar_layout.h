@@ -25,6 +25,11 @@ static inline int agar_layout_compute(const AgarConfig* c, AgarLayout* L) {
     /* VIRUS_GRID without VIRUS_SPAWN: the reference assigns gsVirus = None into the grid, a channel of NaN
      * (bot.py:380-382, 481); networkParameters.py derives VIRUS_GRID from VIRUS_SPAWN, so only a hand-edited file gets here */
     if (c->virus_grid && !c->virus_enabled) return AGAR_E_UNSUPPORTED;
+    /* ALL_PLAYER_GRID replaces the self / enemy grids (networkParameters.py:89-91); with both, the reference stores None
+     * (NaN) channels and None history grids (bot.py:372-378, 483-494) */
+    if (c->all_player_grid && (c->self_grid || c->enemy_grid || c->self_grid_lf || c->self_grid_slf || c->enemy_grid_lf ||
+                               c->enemy_grid_slf))
+        return AGAR_E_UNSUPPORTED;
     int n_agents = 0;
     for (int k = 0; k < K; ++k) {
         int t = c->bot_type[k];
@@ -58,7 +63,7 @@ static inline int agar_layout_compute(const AgarConfig* c, AgarLayout* L) {
     /* networkParameters.py:98-102 */
     L->n_grids = (c->pellet_grid != 0) + (c->self_grid != 0) + (c->wall_grid != 0) + (c->virus_grid != 0) +
                  (c->enemy_grid != 0) + (c->self_grid_lf != 0) + (c->self_grid_slf != 0) + (c->enemy_grid_lf != 0) +
-                 (c->enemy_grid_slf != 0);
+                 (c->enemy_grid_slf != 0) + (c->all_player_grid != 0);
     L->n_extra = (c->use_fovsize != 0) + (c->use_totalmass != 0) + 4 * (c->use_last_action != 0) +
                  4 * (c->use_second_last_action != 0) + (c->use_last_fovsize != 0);
     L->state_len = c->grid_squares * c->grid_squares * L->n_grids + L->n_extra;

@@ -993,6 +993,10 @@ static void observe_agent(OracleEnv* e, int k, int agent, float* obs, double* ob
     if (cf->self_grid) EMIT(own);
     if (cf->wall_grid) EMIT(wall);
     if (cf->enemy_grid) EMIT(enemy);
+    if (cf->all_player_grid) { /* bot.py:348-351, 407-413, 472-474: biggest cell of any player in the square */
+        for (int i = 0; i < GG; ++i) out[n + i] = own[i] > enemy[i] ? own[i] : enemy[i];
+        n += GG;
+    }
     if (cf->virus_grid) EMIT(vir);
     if (cf->self_grid_slf) {
         EMITF(hist + 1 * GG);

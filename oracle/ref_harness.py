@@ -390,7 +390,7 @@ def make_params(cfg):
     flags = {"PELLET_GRID": cfg.pellet_grid, "SELF_GRID": cfg.self_grid, "WALL_GRID": cfg.wall_grid,
              "ENEMY_GRID": cfg.enemy_grid, "VIRUS_GRID": cfg.virus_grid, "SELF_GRID_LF": cfg.self_grid_lf,
              "SELF_GRID_SLF": cfg.self_grid_slf, "ENEMY_GRID_LF": cfg.enemy_grid_lf,
-             "ENEMY_GRID_SLF": cfg.enemy_grid_slf, "USE_FOVSIZE": cfg.use_fovsize,
+             "ENEMY_GRID_SLF": cfg.enemy_grid_slf, "ALL_PLAYER_GRID": cfg.all_player_grid, "USE_FOVSIZE": cfg.use_fovsize,
              "USE_LAST_FOVSIZE": cfg.use_last_fovsize, "USE_TOTALMASS": cfg.use_totalmass,
              "USE_LAST_ACTION": cfg.use_last_action, "USE_SECOND_LAST_ACTION": cfg.use_second_last_action}
     for k, v in flags.items():

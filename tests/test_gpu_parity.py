@@ -43,6 +43,8 @@ VARIATIONS = [
     (dict(grid=42, overrides={"use_fovsize": 0, "use_totalmass": 0}), None), (dict(grid=63), None), (dict(grid=20, obs_mode=1), None),
     (dict(grid=42, num_nn=1, num_greedy=1, virus=True, split=True, eject=True), 32),
     (dict(grid=42, num_nn=2, num_greedy=2, virus=True, split=True, eject=True, obs_mode=1), 32),
+    # ALL_PLAYER_GRID (networkParameters.py:88-91)
+    (dict(num_nn=2, num_greedy=1, virus=True, split=True, eject=True, overrides={"all_player_grid": 1, "self_grid": 0, "enemy_grid": 0, "self_grid_lf": 0, "enemy_grid_lf": 0}), 32), (dict(overrides={"all_player_grid": 1}), None),
 ]
 
 

@@ -20,6 +20,9 @@ for case in range(N):
               grid=rnd.choice([3, 5, 8, 11, 11, 14, 16, 19, 25]), frame_skip=rnd.choice([0, 1, 3, 7, 7, 9]),
               obs_mode=rnd.choice([0, 0, 1]), mass_as_reward=rnd.random() < 0.2,
               overrides={f: int(rnd.random() < 0.5) for f in rnd.sample(FLAGS, rnd.randint(0, 6))})
+    if rnd.random() < 0.15:  # ALL_PLAYER_GRID replaces the self / enemy channels (networkParameters.py:88-91)
+        kw["overrides"].update({"all_player_grid": 1, "self_grid": 0, "enemy_grid": 0, "self_grid_lf": 0, "self_grid_slf": 0,
+                                "enemy_grid_lf": 0, "enemy_grid_slf": 0})
     try:
         import aigar_b200.layout as lay
         lay.layout_for_config(lay.derive_config(**kw))
