@@ -140,10 +140,48 @@ DEV void axis_buckets2_bits(double p, double radius, double fov, double gs, doub
     b0 = x0 <= lim ? c0 : -1;
     b1 = (x1 <= lim && c1 != c0) ? c1 : -1;
 }
+/* axis_buckets for grids of more than 64 columns (CNN_INPUT_DIM_2 = 84): the same arithmetic, two mask words */
+DEV void axis_buckets_wide(double p, double radius, double fov, double gs, double inv, bool canon, unsigned long long& lo,
+                           unsigned long long& hi) {
+    lo = hi = 0ull;
+    auto set = [&](int col) {
+        if (col < 64) lo |= 1ull << col;
+        else hi |= 1ull << (col - 64);
+    };
+    if (canon) {
+        double l = py_max0(p - radius), h = (p + radius < fov - 1) ? p + radius : fov - 1;
+        if (h < 0) return;
+        int b0 = exact_floor_div(l, gs, inv), b1 = exact_floor_div(h, gs, inv);
+        for (int b = b0; b <= b1 && b < 128; ++b) set(b);
+        return;
+    }
+    double cl = py_max0(p - radius);
+    double q = floor(cl * inv);
+    double res = fma(-q, gs, cl);
+    q = res < 0 ? q - 1 : (res >= gs ? q + 1 : q);
+    double x = q * gs;
+    const double lim = (p + radius < fov - 1) ? p + radius : fov - 1;
+    while (x <= lim) {
+        set(bucket_of_edge(x, gs, inv));
+        x += gs;
+    }
+}
 /* calls f(id) once per distinct bucket of the object (ids is a set in the reference) */
 template <class F>
 DEV void for_each_fov_bucket(double ox, double oy, double radius, double left, double top, double fov, double gs,
                              double inv, int cols, bool canon, F f) {
+    if (cols > 64) { /* uniform per observation */
+        unsigned long long mx[2], my[2];
+        axis_buckets_wide(ox - left, radius, fov, gs, inv, canon, mx[0], mx[1]);
+        axis_buckets_wide(oy - top, radius, fov, gs, inv, canon, my[0], my[1]);
+        for (int hx = 0; hx < 2; ++hx)
+            for (unsigned long long a = mx[hx]; a; a &= a - 1) {
+                int col = 64 * hx + __ffsll((long long)a) - 1;
+                for (int hy = 0; hy < 2; ++hy)
+                    for (unsigned long long t = my[hy]; t; t &= t - 1) f(col + (64 * hy + __ffsll((long long)t) - 1) * cols);
+            }
+        return;
+    }
     unsigned long long mx = axis_buckets(ox - left, radius, fov, gs, inv, canon);
     const unsigned long long my = axis_buckets(oy - top, radius, fov, gs, inv, canon);
     while (mx) {

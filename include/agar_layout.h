@@ -18,7 +18,7 @@ static inline int agar_layout_compute(const AgarConfig* c, AgarLayout* L) {
     memset(L, 0, sizeof(*L));
     int K = c->n_players;
     if (K < 1 || K > AGAR_MAX_PLAYERS) return AGAR_E_INVALID;
-    if (c->grid_squares < 1 || c->grid_squares > 63) return AGAR_E_INVALID;
+    if (c->grid_squares < 1 || c->grid_squares > 84) return AGAR_E_INVALID;
     if (c->frame_skip < 0) return AGAR_E_INVALID;
     if (c->enable_greedy_split) return AGAR_E_UNSUPPORTED;
     if (c->enable_eject && !c->enable_split) return AGAR_E_UNSUPPORTED; /* reference raises TypeError, bot.py:568 */

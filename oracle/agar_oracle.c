@@ -830,7 +830,7 @@ static int in_fov(double x, double y, double r, double fx, double fy, double fov
 }
 
 /* ------------------------------------------------------------------ grid vision (bot.py:326-497, spatialHashTable.py:85-112) */
-#define AGAR_GRID_NB (65 * 65) /* (G + 1)^2 buckets, G <= 63 (agar_layout.h) */
+#define AGAR_GRID_NB (85 * 85) /* (G + 1)^2 buckets, G <= 84 (agar_layout.h) */
 typedef struct GridTables {
     int cols, canonical;
     double pel_sum[AGAR_GRID_NB];
@@ -976,7 +976,7 @@ static void observe_agent(OracleEnv* e, int k, int agent, float* obs, double* ob
         midy += gs;
     }
     /* channel order bot.py:458-495 */
-    static __thread double out[11 * 63 * 63 + 16];
+    static __thread double out[11 * 84 * 84 + 16];
     int n = 0;
     float* hist = e->L.n_hist ? e->hist + (size_t)agent * e->L.n_hist * GG : NULL;
 #define EMIT(src)                                      \

@@ -43,6 +43,9 @@ VARIATIONS = [
     (dict(grid=42, overrides={"use_fovsize": 0, "use_totalmass": 0}), None), (dict(grid=63), None), (dict(grid=20, obs_mode=1), None),
     (dict(grid=42, num_nn=1, num_greedy=1, virus=True, split=True, eject=True), 32),
     (dict(grid=42, num_nn=2, num_greedy=2, virus=True, split=True, eject=True, obs_mode=1), 32),
+    # CNN_INPUT_DIM_2 = 84: more than 64 bucket columns (two mask words)
+    (dict(grid=84, overrides={"use_fovsize": 0, "use_totalmass": 0}), None), (dict(grid=84, num_nn=1, num_greedy=1, virus=True, split=True, eject=True), 32),
+    (dict(grid=70, obs_mode=1), None),
     # ALL_PLAYER_GRID (networkParameters.py:88-91)
     (dict(num_nn=2, num_greedy=1, virus=True, split=True, eject=True, overrides={"all_player_grid": 1, "self_grid": 0, "enemy_grid": 0, "self_grid_lf": 0, "enemy_grid_lf": 0}), 32), (dict(overrides={"all_player_grid": 1}), None),
 ]
@@ -265,7 +268,7 @@ def test_error_behaviour(torch_cuda):
     assert b"rejected" in lib.agar_last_error(None)
     nan_cfg = lay.derive_config(overrides={"virus_grid": 1})   # the reference would emit a NaN channel (bot.py:380-382)
     assert lib.agar_create(ctypes.byref(nan_cfg), 4, 0, 0, 0, None, ctypes.byref(h)) == -4
-    cfg = lay.derive_config(grid=64)     # bucket columns are a 64-bit mask: G <= 63 (CNN_INPUT_DIM_2 = 84 is not covered)
+    cfg = lay.derive_config(grid=85)     # G <= 84 = CNN_INPUT_DIM_2, the largest grid of the reference
     assert lib.agar_create(ctypes.byref(cfg), 4, 0, 0, 0, None, ctypes.byref(h)) == -1
     cnn = AgarBatch(lay.derive_config(grid=42), 4)
     with pytest.raises(AgarError):

@@ -57,6 +57,7 @@ VARIATIONS = [
     dict(grid=42, overrides={"use_fovsize": 0, "use_totalmass": 0}),   # the handcraft-CNN grid (bot.py:103-111), §8f rank 3
     dict(grid=42, num_nn=1, num_greedy=1, virus=True, split=True, eject=True),
     dict(grid=63),
+    dict(grid=84, overrides={"use_fovsize": 0, "use_totalmass": 0}),   # CNN_INPUT_DIM_2
     # ALL_PLAYER_GRID (networkParameters.py:88-91): one "biggest cell of any player" channel instead of self / enemy
     dict(num_nn=1, num_greedy=1, virus=True, split=True, eject=True, overrides={"all_player_grid": 1, "self_grid": 0, "enemy_grid": 0, "self_grid_lf": 0, "enemy_grid_lf": 0}),
     dict(overrides={"all_player_grid": 1}),
