@@ -70,6 +70,8 @@ def test_config_variations_equal_reference(kw):
     channel subsets, bot mixes."""
     import compare_oracle_ref as cmp
     frames = 160 if kw.get("num_nn", 1) + kw.get("num_greedy", 0) + kw.get("num_random", 0) <= 2 else 90
+    if kw.get("grid", 11) >= 42:
+        frames = 48  # the reference's encoder is O(G^2) Python per observation
     assert cmp.run(kw, frames, seed=31, verbose=False)
 
 
