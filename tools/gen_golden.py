@@ -23,6 +23,11 @@ CASES = {
     # (src/model/bot.py:103-111,276-282; networkParameters.py:195-208)
     "cnn42_pellet_canonical": (dict(grid=42, obs_mode=1, overrides={"use_fovsize": 0, "use_totalmass": 0}), 320, 11, 3, 80),
     "cnn42_1v1": (dict(grid=42, num_nn=1, num_greedy=1, virus=True, split=True, eject=True), 160, 13, 1, 40),
+    "cnn84_pellet_canonical": (dict(grid=84, obs_mode=1, overrides={"use_fovsize": 0, "use_totalmass": 0}), 96, 15, 2, 48),
+    # ALL_PLAYER_GRID (networkParameters.py:88-91) instead of the self / enemy channels
+    "all_player_1v1_canonical": (dict(num_nn=1, num_greedy=1, virus=True, split=True, eject=True, obs_mode=1,
+                                      overrides={"all_player_grid": 1, "self_grid": 0, "enemy_grid": 0, "self_grid_lf": 0,
+                                                 "enemy_grid_lf": 0}), 320, 17, 3, 80),
 }
 
 
