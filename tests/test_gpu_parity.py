@@ -433,3 +433,20 @@ def test_step_host_pinned_buffers_equal_pageable(torch_cuda):
                 assert np.array_equal(x.numpy(), y)
         assert a.launch_count - launches0 == 20          # step kernel + export kernel per call
         assert torch.equal(a.state_tensor(), b.state_tensor())
+
+
+@pytest.mark.parametrize("kw,n_envs", [(dict(num_nn=1, num_greedy=1, virus=True, split=True, eject=True), 4736),
+                                       (dict(num_nn=8, num_greedy=8, virus=True, split=True, eject=True), 600)])
+def test_multi_agent_results_do_not_depend_on_launch_shape(torch_cuda, kw, n_envs):
+    """One batch against three shards with other tile widths / envs per CTA (1024-, 768- and 512-thread variants of
+    k_main, wave-aware CTA sizing): identical records after 320 frames — RNG keys use global env ids."""
+    torch = torch_cuda
+    from aigar_b200.env import AgarBatch
+    cfg = lay.derive_config(**kw)
+    whole = AgarBatch(cfg, n_envs, seed=3, first_env_id=0)
+    h = n_envs // 3
+    parts = [AgarBatch(cfg, n, seed=3, first_env_id=f, tile_width=w)
+             for f, n, w in ((0, h, None), (h, h, 16), (2 * h, n_envs - 2 * h, None))]
+    for b in [whole] + parts:
+        b.rollout_random(40, 8, 0)
+    assert torch.equal(whole.state_tensor(), torch.cat([p.state_tensor() for p in parts], 0))
