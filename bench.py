@@ -330,8 +330,9 @@ def main():
         except Exception as ex:
             extra["obs_every_frame"] = {"error": str(ex)[:200]}
         # BASELINE configs[2] / [3] (parity-test cases, reported for reference): multi-agent kernels, 96-frame launches
-        for name, kw, En in (("config3_1v1_greedy_16384", dict(num_nn=1, num_greedy=1, virus=True, split=True, eject=True), 16384),
-                             ("config4_arena_8192", dict(num_nn=8, num_greedy=8, virus=True, split=True, eject=True), 8192)):
+        # algorithmic bytes per env-step: SURVEY §8d's worked figures for these configs (obs every 8th frame)
+        for name, kw, En, bpe in (("config3_1v1_greedy_16384", dict(num_nn=1, num_greedy=1, virus=True, split=True, eject=True), 16384, 2950.0),
+                                  ("config4_arena_8192", dict(num_nn=8, num_greedy=8, virus=True, split=True, eject=True), 8192, 22900.0)):
             try:
                 cm = lay.derive_config(**kw)
                 bm = AgarBatch(cm, En, device=local, seed=2026, first_env_id=3 * 10 ** 6)
@@ -345,7 +346,9 @@ def main():
                     torch.cuda.synchronize()
                     ts.append(s.elapsed_time(e))
                 ms = sum(ts) / len(ts)
-                extra[name] = {"value": En * 12 * PERIOD / (ms * 1e-3), "unit": UNIT, "ms_per_launch": ms, "frames_per_launch": 12 * PERIOD,
+                vm = En * 12 * PERIOD / (ms * 1e-3)
+                extra[name] = {"value": vm, "unit": UNIT, "ms_per_launch": ms, "frames_per_launch": 12 * PERIOD,
+                               "bytes_per_env_step": bpe, "roofline_frac": vm * bpe / 1e9 / measured_peak()[0],
                                "players": int(bm.layout.n_players), "state_len": int(bm.layout.state_len), "tile_width": bm.tile_width}
                 bm.close()
             except Exception as ex:
