@@ -122,6 +122,10 @@ k_main(const __grid_constant__ DevParams P, uint8_t* __restrict__ state, const f
             const int f = n_frames > 0 ? it % n_frames : 0, d = n_frames > 0 ? it / n_frames : 0;
             const bool emit = last || (f == 0 && (flags & KF_OBS_BEFORE)); /* observations leave the kernel here */
             if (active && !last && c.lane == 0) c.h->n_events = 0;
+            if (FULL && K > 1 && active && !last) { /* every alive player's turn below would compute its own, on lane 0 */
+                update_all_fovs(c, P);
+                c.fov_done = true;
+            }
             for (int k = 0; k < K; ++k) {
                 if (psync_bots && k > 0) __syncthreads(); /* one bot turn per barrier interval */
                 if (active) {
@@ -150,6 +154,7 @@ k_main(const __grid_constant__ DevParams P, uint8_t* __restrict__ state, const f
                 }
             }
             if (last) break;
+            c.fov_done = false;
             for (int ph = 0; ph < AGAR_FIELD_PHASES; ++ph) {
                 if (ph == 0 ? psync : psync_field) __syncthreads();
                 if (active) field_update_phase<W, FULL>(c, P, ph);

@@ -237,7 +237,7 @@ DEV void observe_agent(Ctx<W>& c, const DevParams& P, int k, int agent, float* o
     AgarPlayer* p = &c.pl[k];
     const int G = P.L.grid_squares, GG = G * G;
     const double S = (double)P.S;
-    if (c.lane == 0) update_fov(c, P, k);
+    if (c.lane == 0 && !c.fov_done) update_fov(c, P, k);
     c.t.sync();
     const double fov = p->fov_size, fx = p->fov_x, fy = p->fov_y;
     const double left = fx - fov / 2, top = fy - fov / 2;
@@ -427,7 +427,7 @@ template <int W>
 DEV void set_command_point(Ctx<W>& c, const DevParams& P, int k, double a0, double a1, double a2, double a3, int len,
                            bool fov_fresh) {
     AgarPlayer* p = &c.pl[k];
-    if (!fov_fresh) update_fov(c, P, k); /* fresh: computed a moment ago in this bot turn from the same cells */
+    if (!fov_fresh && !c.fov_done) update_fov(c, P, k); /* fresh: computed a moment ago in this bot turn from the same cells */
     int x = (int)p->fov_x, y = (int)p->fov_y;
     int left = x - (int)(p->fov_size / 2), top = y - (int)(p->fov_size / 2);
     int size = (int)p->fov_size;
@@ -515,7 +515,7 @@ DEV void scripted_turn(Ctx<W>& c, const DevParams& P, int k) {
         B->stat_mass_sum += tm;
         if (tm > B->stat_mass_max) B->stat_mass_max = tm;
         B->stat_frames += 1;
-        if (p->alive) update_fov(c, P, k);
+        if (p->alive && !c.fov_done) update_fov(c, P, k);
     }
     c.t.sync();
     if (!p->alive) return; /* uniform: nothing below changes alive */

@@ -69,7 +69,8 @@ struct Ctx {
     float* hist;
     AgarEvent* ev;
     uint8_t* scratch;
-    __device__ Ctx(cg::thread_block_tile<W> tile) : t(tile) {}
+    bool fov_done; /* this frame's fields of view were computed up front for every player (update_all_fovs) */
+    __device__ Ctx(cg::thread_block_tile<W> tile) : t(tile), fov_done(false) {}
 };
 
 #define CELLP(c, P, k, i) (&(c).cells[(k) * (P).L.cell_cap + (i)])
@@ -239,6 +240,14 @@ DEV void update_fov(Ctx<W>& c, const DevParams& P, int k) {
     for (int i = 1; i < n; ++i)
         if (base[i].radius > rmax) rmax = base[i].radius;
     p->fov_size = agar_pow(rmax, 0.475) * P.pow_n[n] * 35;
+}
+/* cooperative: the fields of view of ALL players at once, lane k for player k.  Every alive player's bot turn computes
+ * them from the same cells (bot turns only set command points and split / eject flags), so K sequential lane-0 passes
+ * — a `pow`, two pairwise sums and a mass total each — become one pass with K lanes busy. */
+template <int W>
+DEV void update_all_fovs(Ctx<W>& c, const DevParams& P) {
+    for (int k = c.lane; k < P.L.n_players; k += W) update_fov(c, P, k);
+    c.t.sync();
 }
 template <int W>
 DEV void cell_remove(Ctx<W>& c, const DevParams& P, int k, int i) {
