@@ -125,6 +125,7 @@ k_main(const __grid_constant__ DevParams P, uint8_t* __restrict__ state, const f
             if (FULL && K > 1 && active && !last) { /* every alive player's turn below would compute its own, on lane 0 */
                 update_all_fovs(c, P);
                 c.fov_done = true;
+                if (K * P.L.cell_cap > W) build_live_cells(c, P); /* one iteration covers all slots otherwise */
             }
             for (int k = 0; k < K; ++k) {
                 if (psync_bots && k > 0) __syncthreads(); /* one bot turn per barrier interval */
@@ -154,7 +155,7 @@ k_main(const __grid_constant__ DevParams P, uint8_t* __restrict__ state, const f
                 }
             }
             if (last) break;
-            c.fov_done = false;
+            c.fov_done = false, c.n_live = -1;
             for (int ph = 0; ph < AGAR_FIELD_PHASES; ++ph) {
                 if (ph == 0 ? psync : psync_field) __syncthreads();
                 if (active) field_update_phase<W, FULL>(c, P, ph);
@@ -617,6 +618,8 @@ extern "C" int agar_create(const AgarConfig* cfg, int n_envs, int device, uint64
     int vel_bytes = e->full ? L.n_players * L.cell_cap * 2 * 8 : 0;
     int obs_bytes = obs_scratch_bytes(L.grid_squares, e->full != 0);
     P.scratch_bytes = ((vel_bytes > obs_bytes ? vel_bytes : obs_bytes) + 15) / 16 * 16 + 8;
+    P.live_off = P.scratch_bytes; /* live-cell list: uint16 per cell slot, after the observation / velocity scratch */
+    if (e->full) P.scratch_bytes += (L.n_players * L.cell_cap * 2 + 15) / 16 * 16;
     /* Where a record lives during a launch.  1: whole record staged in shared memory (single-cell general kernel).
      * Multi-agent configs keep the record in HBM / L2 and cache on chip what every scan and lane-0 step reads:
      * 3 = header + players + cells + viruses + pellet pool if at least 12 envs per CTA still fit, else 2 = the pellet

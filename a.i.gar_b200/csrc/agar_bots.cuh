@@ -330,7 +330,10 @@ DEV void observe_agent(Ctx<W>& c, const DevParams& P, int k, int agent, float* o
             c.t.sync();
             for (int i = c.lane; i < nbk; i += W) tabu[i] = 0ull;
             c.t.sync();
-            for (int idx = c.lane; idx < K * cap; idx += W) {
+            const uint16_t* live = live_cells(c, P);
+            const int n_it = c.n_live >= 0 ? c.n_live : K * cap;
+            for (int t = c.lane; t < n_it; t += W) {
+                int idx = c.n_live >= 0 ? (int)live[t] : t;
                 int k2 = idx / cap, j = idx - k2 * cap;
                 if ((!all && (k2 == k) != own) || j >= c.pl[k2].n_cells) continue;
                 const AgarCell* o = CELLP(c, P, k2, j);
@@ -553,7 +556,10 @@ DEV void scripted_turn(Ctx<W>& c, const DevParams& P, int k) {
         }
         ord0 += P.L.fat_cap;
         const int K = P.L.n_players, cap = P.L.cell_cap;
-        for (int idx = c.lane; idx < K * cap; idx += W) {
+        const uint16_t* live = live_cells(c, P);
+        const int n_it = c.n_live >= 0 ? c.n_live : K * cap;
+        for (int t = c.lane; t < n_it; t += W) {
+            int idx = c.n_live >= 0 ? (int)live[t] : t;
             int k2 = idx / cap, j = idx - k2 * cap;
             if (k2 == k || j >= c.pl[k2].n_cells) continue;
             const AgarCell* o = CELLP(c, P, k2, j);

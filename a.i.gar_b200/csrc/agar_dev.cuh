@@ -44,7 +44,7 @@ struct DevParams {
     double pow_n[17];
     const double* deg_tab; /* cos(d*pi/180)[360], sin(...)[360] — host libm, exactly the oracle's table */
     uint64_t seed, first_env;
-    int hot_a, pad2; /* stage >= 2: bytes [0, hot_a) of a record (header, players, cells, viruses) are cached in shared memory too */
+    int hot_a, live_off; /* live_off: offset of the live-cell list in a tile's scratch (multi-agent configs) */ /* stage >= 2: bytes [0, hot_a) of a record (header, players, cells, viruses) are cached in shared memory too */
     /* optional per-launch outputs of the last bot turn ([E][A]); NULL = use agar_get */
     float* turn_reward;
     uint8_t* turn_done;
@@ -70,7 +70,8 @@ struct Ctx {
     AgarEvent* ev;
     uint8_t* scratch;
     bool fov_done; /* this frame's fields of view were computed up front for every player (update_all_fovs) */
-    __device__ Ctx(cg::thread_block_tile<W> tile) : t(tile), fov_done(false) {}
+    int n_live;    /* >= 0: live_cells() lists the (player * cell_cap + cell) indices of all live cells, canonical order */
+    __device__ Ctx(cg::thread_block_tile<W> tile) : t(tile), fov_done(false), n_live(-1) {}
 };
 
 #define CELLP(c, P, k, i) (&(c).cells[(k) * (P).L.cell_cap + (i)])
@@ -247,6 +248,26 @@ DEV void update_fov(Ctx<W>& c, const DevParams& P, int k) {
 template <int W>
 DEV void update_all_fovs(Ctx<W>& c, const DevParams& P) {
     for (int k = c.lane; k < P.L.n_players; k += W) update_fov(c, P, k);
+    c.t.sync();
+}
+/* cooperative: compact list of the live cells (of 16 x 16 slots, ~24 are live in the arena), valid while no cell is
+ * created or removed — the bot phase.  Loops over "every cell of every player" then run one or two full-width
+ * iterations instead of eight nearly empty ones. */
+template <int W>
+DEV const uint16_t* live_cells(const Ctx<W>& c, const DevParams& P) { return (const uint16_t*)(c.scratch + P.live_off); }
+template <int W>
+DEV void build_live_cells(Ctx<W>& c, const DevParams& P) {
+    uint16_t* live = (uint16_t*)(c.scratch + P.live_off);
+    const int cap = P.L.cell_cap, total = P.L.n_players * cap;
+    int n = 0;
+    for (int base = 0; base < total; base += W) {
+        int idx = base + c.lane, k2 = idx / cap, j = idx - k2 * cap;
+        bool on = idx < total && j < c.pl[k2].n_cells;
+        unsigned b = c.t.ballot(on);
+        if (on) live[n + __popc(b & ((1u << c.lane) - 1))] = (uint16_t)idx;
+        n += __popc(b);
+    }
+    c.n_live = n;
     c.t.sync();
 }
 template <int W>
