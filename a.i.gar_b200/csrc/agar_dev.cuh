@@ -1009,8 +1009,11 @@ template <int W>
 DEV bool any_player_mote_hit(Ctx<W>& c, const DevParams& P, const AgarMote* motes, int n, bool is_virus) {
     const int K = P.L.n_players, cap = P.L.cell_cap;
     bool hit = false;
+    const uint16_t* live = live_cells(c, P);
+    const int n_it = c.n_live >= 0 ? c.n_live : K * cap;
     if (n > 0)
-        for (int idx = c.lane; idx < K * cap && !hit; idx += W) {
+        for (int t = c.lane; t < n_it && !hit; t += W) {
+            int idx = c.n_live >= 0 ? (int)live[t] : t;
             int k = idx / cap, i = idx - k * cap;
             if (!c.pl[k].alive || i >= c.pl[k].n_cells) continue;
             const AgarCell* q = CELLP(c, P, k, i);
@@ -1029,7 +1032,10 @@ template <int W>
 DEV bool any_player_player_hit(Ctx<W>& c, const DevParams& P) {
     const int K = P.L.n_players, cap = P.L.cell_cap;
     bool hit = false;
-    for (int idx = c.lane; idx < K * cap && !hit; idx += W) {
+    const uint16_t* live = live_cells(c, P);
+    const int n_it = c.n_live >= 0 ? c.n_live : K * cap;
+    for (int t = c.lane; t < n_it && !hit; t += W) {
+        int idx = c.n_live >= 0 ? (int)live[t] : t;
         int k = idx / cap, i = idx - k * cap;
         if (!c.pl[k].alive || i >= c.pl[k].n_cells) continue;
         const AgarCell* q = CELLP(c, P, k, i);
@@ -1079,7 +1085,11 @@ DEV void field_update_phase(Ctx<W>& c, const DevParams& P, int phase) {
                 if (c.lane == 0) virus_blob_overlap_seq(c, P);
                 c.t.sync();
             }
-            if (any_player_mote_hit(c, P, c.vir, c.h->n_viruses, true)) {
+            const bool use_live = P.L.n_players * P.L.cell_cap > W; /* cells are stable from here to the seq passes */
+            if (use_live && c.h->n_viruses > 0) build_live_cells(c, P);
+            bool vh = any_player_mote_hit(c, P, c.vir, c.h->n_viruses, true);
+            c.n_live = -1;
+            if (vh) {
                 if (c.lane == 0) player_virus_overlap_seq(c, P);
                 c.t.sync();
             }
@@ -1097,11 +1107,15 @@ DEV void field_update_phase(Ctx<W>& c, const DevParams& P, int phase) {
         }
     } else {
         if (FULL) {
+            /* pellet and blob eating change masses, not the set of cells: one live list serves both pre-checks */
+            if (P.L.n_players * P.L.cell_cap > W && (c.h->n_blobs > 0 || P.L.n_players > 1)) build_live_cells(c, P);
             if (any_player_mote_hit(c, P, c.blob, c.h->n_blobs, false)) {
                 if (c.lane == 0) player_blob_overlap_seq(c, P);
                 c.t.sync();
             }
-            if (P.L.n_players > 1 && any_player_player_hit(c, P)) {
+            bool ph = P.L.n_players > 1 && any_player_player_hit(c, P);
+            c.n_live = -1;
+            if (ph) {
                 if (c.lane == 0) player_player_overlap_seq(c, P);
                 c.t.sync();
             }
