@@ -9,7 +9,7 @@ SRC_REPLAY = os.path.join(_HERE, "csrc", "agar_replay.cu")
 LIB = os.path.join(_HERE, "libagar_b200.so")
 DEPS = [SRC, SRC_REPLAY, os.path.join(_HERE, "csrc", "agar_dev.cuh"), os.path.join(_HERE, "csrc", "agar_bots.cuh"),
         os.path.join(_HERE, "csrc", "agar_simple.cuh")] + [
-    os.path.join(os.path.dirname(_HERE), "include", n) for n in ("agar_b200.h", "agar_layout.h", "agar_math.h", "agar_replay.h")]
+    os.path.join(os.path.dirname(_HERE), "include", n) for n in ("agar_b200.h", "agar_layout.h", "agar_math.h", "agar_libm_tables.h", "agar_replay.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC"]

@@ -412,7 +412,6 @@ struct AgarEnv {
     void* h_turn; /* pinned */
     int host_pending; /* agar_step_host_begin issued, _end not yet */
     int host_zerocopy; /* pinned caller buffers are read / written in place (AGAR_HOST_ZEROCOPY=0 disables) */
-    long long attr_main, attr_simple; /* launch shapes whose max-dynamic-shared-memory attribute is already set */
 };
 static char g_create_err[256] = "";
 
@@ -472,16 +471,27 @@ static bool plan_launch(AgarEnv* e, int W) {
     return true;
 }
 
+/* cudaFuncSetAttribute is per kernel FUNCTION and process-wide, not per handle: two handles with different shared-memory
+ * needs (a training batch and an evaluation batch of the same config) must not lower each other's limit.  Every
+ * instantiation is therefore raised ONCE per device to the device's opt-in maximum (the launch itself still requests only
+ * what it needs, so occupancy is unaffected).  `done` is a per-instantiation static; setting twice is harmless. */
+template <typename K>
+static cudaError_t ensure_max_smem(K kernel, int device, unsigned char* done) {
+    if (device >= 0 && device < 64 && done[device]) return cudaSuccess;
+    int optin = 0;
+    cudaError_t err = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    if (err != cudaSuccess) return err;
+    err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    if (err == cudaSuccess && device >= 0 && device < 64) done[device] = 1;
+    return err;
+}
+
 template <int W, bool FULL, int MAXT>
 static cudaError_t launch_main_k(AgarEnv* e, const float* actions, float* obs, int n_frames, int n_dec, int flags,
                                  uint32_t dec_base, cudaStream_t s) {
-    cudaError_t err = cudaSuccess;
-    const long long key = (long long)W * (1ll << 32) + (long long)e->smem_bytes + ((long long)MAXT << 40);
-    if (e->attr_main != key) { /* once per launch shape, not per launch */
-        err = cudaFuncSetAttribute(k_main<W, FULL, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes);
-        if (err != cudaSuccess) return err;
-        e->attr_main = key;
-    }
+    static unsigned char done[64];
+    cudaError_t err = ensure_max_smem(k_main<W, FULL, MAXT>, e->device, done);
+    if (err != cudaSuccess) return err;
     int blocks = (e->n_envs + e->tiles - 1) / e->tiles;
     k_main<W, FULL, MAXT><<<blocks, e->threads, e->smem_bytes, s>>>(e->P, e->state, actions, obs, n_frames, n_dec, flags, dec_base);
     return cudaGetLastError();
@@ -495,7 +505,8 @@ static cudaError_t launch_main_t(AgarEnv* e, const float* actions, float* obs, i
 }
 template <int W, bool FULL>
 static cudaError_t launch_init_t(AgarEnv* e, const uint8_t* mask, int mode, cudaStream_t s) {
-    cudaError_t err = cudaFuncSetAttribute(k_init<W, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->init_smem);
+    static unsigned char done[64];
+    cudaError_t err = ensure_max_smem(k_init<W, FULL>, e->device, done);
     if (err != cudaSuccess) return err;
     int blocks = (e->n_envs + e->init_tiles - 1) / e->init_tiles;
     k_init<W, FULL><<<blocks, e->init_threads, e->init_smem, s>>>(e->P, e->state, mask, mode);
@@ -518,11 +529,8 @@ static int launch_main(AgarEnv* e, const float* actions, float* obs, int n_frame
         int blocks = (e->n_envs * e->simple_W + e->simple_threads - 1) / e->simple_threads;
 #define LAUNCH_SIMPLE(WW)                                                                                                     \
     do {                                                                                                                      \
-        err = cudaSuccess;                                                                                                    \
-        if (e->attr_simple != (long long)WW * (1ll << 32) + (long long)e->simple_smem) {                                      \
-            err = cudaFuncSetAttribute(k_simple<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->simple_smem);       \
-            if (err == cudaSuccess) e->attr_simple = (long long)WW * (1ll << 32) + (long long)e->simple_smem;                 \
-        }                                                                                                                     \
+        static unsigned char done_##WW[64];                                                                                   \
+        err = ensure_max_smem(k_simple<WW>, e->device, done_##WW);                                                            \
         if (err == cudaSuccess) {                                                                                             \
             k_simple<WW><<<blocks, e->simple_threads, e->simple_smem, (cudaStream_t)stream>>>(e->P, e->sp, e->state, actions, obs, \
                                                                                               n_frames, n_dec, flags, dec_base);  \

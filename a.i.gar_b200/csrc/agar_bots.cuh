@@ -315,7 +315,7 @@ DEV void observe_agent(Ctx<W>& c, const DevParams& P, int k, int agent, float* o
                 double lb = py_minS(S, py_max0(midx - gs / 2)), tb = py_minS(S, py_max0(midy - gs / 2));
                 double rb = py_max0(py_minS(S, midx + gs / 2)), bb = py_max0(py_minS(S, midy + gs / 2));
                 double free_area = (rb - lb) * (bb - tb);
-                double w = agar_round_dec(1 - (free_area / (gs * gs)), 1e3);
+                double w = agar_round_dec(1 - (free_area / agar_pow(gs, 2.0)), 1e3); /* gsSize ** 2 == C pow */
                 if (obs) obs[ch_wall * GG + idx] = (float)w;
             }
         }

@@ -139,7 +139,7 @@ __global__ void k_rp_init(ReplayDev d) {
         d.mn[i] = INFINITY;
     }
     if (i == 0) {
-        d.counters[0] = d.counters[1] = d.counters[2] = 0;
+        d.counters[0] = d.counters[1] = d.counters[2] = d.counters[3] = 0;
         *d.max_priority = 1.0;
     }
 }
@@ -148,6 +148,10 @@ __global__ void k_rp_gather(ReplayDev d, const int32_t* __restrict__ idx, int ba
     int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= batch) return;
     int p = idx[w];
+    if (p < 0 || p >= d.counters[1]) { /* the reference asserts 0 <= idx < len(storage); here: flag, read slot 0 */
+        if (lane == 0) atomicOr(&d.counters[3], AGAR_RP_ERR_INDEX);
+        p = 0;
+    }
     const float* s0 = d.obs_t + (size_t)p * d.L;
     const float* s1 = d.obs_tp1 + (size_t)p * d.L;
     for (int i = lane; i < d.L; i += 32) {
@@ -164,6 +168,11 @@ __global__ void k_rp_uniform_idx(ReplayDev d, const double* __restrict__ u, int 
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= batch) return;
     int len = d.counters[1];
+    if (len < 1) { /* random.randint(0, -1) raises in the reference; here: index 0 and a sticky error flag */
+        atomicOr(&d.counters[3], AGAR_RP_ERR_EMPTY);
+        idx[i] = 0;
+        return;
+    }
     int v = (int)(u[i] * (double)len); /* random.randint(0, len - 1) */
     idx[i] = v >= len ? len - 1 : v;
 }
@@ -173,6 +182,8 @@ __device__ double rp_prefix_sum(const ReplayDev& d, int end) {
     double parts[40];
     int np = 0;
     int node = 1, ns = 0, ne = d.itcap - 1;
+    if (end < 0) return 0.0; /* callers guard len < 2; never descend with an end the loop cannot reach */
+    if (end > ne) end = ne;
     while (true) {
         if (end == ne) {
             parts[np++] = d.sum[node];
@@ -194,6 +205,12 @@ __global__ void k_rp_per_sample(ReplayDev d, const double* __restrict__ u, int b
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= batch) return;
     const int len = d.counters[1];
+    if (len < 2) { /* the reference recurses without end here (sum(0, len - 1) over an empty prefix); flag and return slot 0 */
+        atomicOr(&d.counters[3], AGAR_RP_ERR_EMPTY);
+        idx[i] = 0;
+        if (weights) weights[i] = 0.0;
+        return;
+    }
     /* _sample_proportional (:113-120): sum(0, len - 1) reduces over [0, len - 2] (reduce() decrements `end`) */
     double total = rp_prefix_sum(d, len - 2);
     double mass = u[i] * total;
@@ -223,6 +240,15 @@ __global__ void k_rp_set_priorities(ReplayDev d, const int32_t* __restrict__ idx
     /* duplicates in idx: the reference applies them in order, the last one wins */
     for (int j = i + 1; j < batch; ++j)
         if (idx[j] == idx[i]) return;
+    /* replay_buffer.py:203-204 asserts priority > 0 and 0 <= idx < len(storage): skip and flag instead of poisoning the trees */
+    if (idx[i] < 0 || idx[i] >= d.counters[1]) {
+        atomicOr(&d.counters[3], AGAR_RP_ERR_INDEX);
+        return;
+    }
+    if (!(prio[i] > 0.0) || prio[i] > 1.7e308) {
+        atomicOr(&d.counters[3], AGAR_RP_ERR_PRIORITY);
+        return;
+    }
     double v = agar_pow(prio[i], d.alpha);
     d.sum[d.itcap + idx[i]] = v;
     d.mn[d.itcap + idx[i]] = v;
@@ -230,7 +256,7 @@ __global__ void k_rp_set_priorities(ReplayDev d, const int32_t* __restrict__ idx
 __global__ void k_rp_max_priority(ReplayDev d, const double* __restrict__ prio, int batch) {
     double m = *d.max_priority;
     for (int i = 0; i < batch; ++i)
-        if (prio[i] > m) m = prio[i];
+        if (prio[i] > m && prio[i] <= 1.7e308) m = prio[i];
     *d.max_priority = m;
 }
 
@@ -290,6 +316,9 @@ static int rp_counter(AgarReplay* rp, int which, void* stream) {
     if (cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) return AGAR_E_CUDA;
     return v;
 }
+/* sticky AGAR_RP_ERR_* bits raised on the device since create (sampling from a buffer that is too small, an index outside
+ * [0, size), a priority <= 0): where the reference raises / asserts, the kernels skip the offending element and flag it */
+extern "C" int agar_replay_error_flags(AgarReplay* rp, void* stream) { return rp ? rp_counter(rp, 3, stream) : AGAR_E_INVALID; }
 extern "C" int agar_replay_size(AgarReplay* rp, void* stream) { return rp ? rp_counter(rp, 1, stream) : AGAR_E_INVALID; }
 extern "C" int agar_replay_next_idx(AgarReplay* rp, void* stream) { return rp ? rp_counter(rp, 0, stream) : AGAR_E_INVALID; }
 

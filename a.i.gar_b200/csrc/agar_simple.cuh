@@ -312,14 +312,7 @@ DEV void s_field_update(SReg& r, const SPtr& q, const DevParams& P, uint32_t env
     double h2 = xd * xd + yd * yd, r2 = radius * radius;
     double sm = (h2 < r2 ? h2 : r2) / r2;
     double cs, sn;
-    if (h2 == 0.0) { /* agar_dir: atan2(0, 0) = 0 -> (1, 0) */
-        cs = 1.0, sn = 0.0;
-    }
-    {
-        double hh = sqrt(h2), c2, s2;
-        s_dual_div<W>(xd, hh, yd, hh, sub, c2, s2);
-        if (h2 != 0.0) cs = c2, sn = s2;
-    }
+    agar_dir(yd, xd, &cs, &sn); /* cell.py:49-57: cos / sin of the ROUNDED angle atan2 returns, bit-identical to libm */
     double rs = P.move_speed * speed_pow; /* = agar_pow(mass, -0.35), evaluated next to the fov pow in s_turn_end */
     double vx = rs * sm * cs, vy = rs * sm * sn;
     update_pos(r.x, r.y, vx, vy, r.svx, r.svy, r.counter, S);

@@ -21,6 +21,7 @@ def _bind(lib):
     lib.agar_replay_sample_uniform.argtypes = [vp, vp, i32, vp] + [vp] * 5 + [vp]
     lib.agar_replay_sample_prioritized.argtypes = [vp, vp, i32, vp, vp] + [vp] * 5 + [vp]
     lib.agar_replay_update_priorities.argtypes = [vp, vp, vp, i32, vp]
+    lib.agar_replay_error_flags.argtypes = [vp, vp]
     lib.agar_replay_launch_count.argtypes = [vp]
     lib.agar_replay_launch_count.restype = ctypes.c_int64
     lib._replay_bound = True
@@ -71,6 +72,18 @@ class GpuReplayBuffer(object):
     @property
     def next_idx(self):
         return int(self.lib.agar_replay_next_idx(self.h, self._stream()))
+
+    @property
+    def error_flags(self):
+        """Sticky AGAR_RP_ERR_* bits (1 sampled a too-small buffer, 2 index out of range, 4 priority <= 0)."""
+        return int(self.lib.agar_replay_error_flags(self.h, self._stream()))
+
+    def raise_on_error(self):
+        """The reference raises / asserts in these cases (replay_buffer.py:66,116,203-204); call after a sync point."""
+        f = self.error_flags
+        if f:
+            raise _env.AgarError("replay buffer error flags %d (1 = sampled from a buffer that is too small, 2 = index out of "
+                                 "range, 4 = priority <= 0)" % f)
 
     @property
     def launch_count(self):

@@ -20,6 +20,7 @@
 #include <stdint.h>
 #include <string.h>
 #include <math.h>
+#include "agar_libm_tables.h"
 
 #ifdef __CUDACC__
 #define AGAR_HD __host__ __device__ __forceinline__
@@ -101,20 +102,253 @@ AGAR_HD double agar_exp(double z) {
     return p * agar_bits_to_double((uint64_t)(ik + 1023) << 52);
 }
 
-/* x^y for x > 0 (the game only raises masses / radii to fixed exponents) */
-AGAR_HD double agar_pow(double x, double y) { return agar_exp(y * agar_log(x)); }
+/* x^y, BIT-IDENTICAL to the pow() CPython's math.pow calls on this image (glibc 2.39, the FMA variant its ifunc
+ * selects on every AVX2+FMA host): the ARM optimized-routines algorithm — log x as a double-double from a 128-entry
+ * table ({1/c, log c} per subinterval, r = x/c - 1 exact in one fma, degree-7 polynomial), times y as a double-double,
+ * then exp from a 128-entry table of 2^(i/128) with a degree-5 polynomial.  It is < 1 ULP but not correctly rounded,
+ * so the operation ORDER and every fma contraction below follow the compiled libm (disassembly of __pow_fma, main
+ * path), not a textbook formula; tables from tools/gen_libm_tables.py.  tests/test_portable_math.py: equal to libm pow
+ * on > 1e8 inputs.  Domain (all the path needs): x positive normal finite; y = 0 or 2^-65 <= |y| < 2^63; |y log x| < 512
+ * is exact-parity, beyond that the result saturates to inf / 0 without glibc's subnormal rounding.
+ * Reference call sites: cell.py:246-248 (mass^-0.35), player.py:163-167 (r^0.475, n^0.32), replay_buffer.py:166-199. */
+#ifdef __CUDACC__
+static __device__ const double agar_pow_log_tab_d[128][3] = {AGAR_POW_LOG_TAB};
+static __device__ const unsigned long long agar_exp_tab_d[256] = {AGAR_EXP_TAB};
+static __device__ const double agar_atan_tab_d[241][7] = {AGAR_ATAN_TAB};
+static __device__ const double agar_sincos_tab_d[440] = {AGAR_SINCOS_TAB};
+#endif
+static const double agar_pow_log_tab_h[128][3] = {AGAR_POW_LOG_TAB};
+static const unsigned long long agar_exp_tab_h[256] = {AGAR_EXP_TAB};
+static const double agar_atan_tab_h[241][7] = {AGAR_ATAN_TAB};
+static const double agar_sincos_tab_h[440] = {AGAR_SINCOS_TAB};
+#ifdef __CUDA_ARCH__
+#define AGAR_POW_LOG_T(i, j) __ldg(&agar_pow_log_tab_d[i][j])
+#define AGAR_EXP_T(i) __ldg(&agar_exp_tab_d[i])
+#define AGAR_ATAN_T(i, j) __ldg(&agar_atan_tab_d[i][j])
+#define AGAR_SINCOS_T(i) __ldg(&agar_sincos_tab_d[i])
+#else
+#define AGAR_POW_LOG_T(i, j) agar_pow_log_tab_h[i][j]
+#define AGAR_EXP_T(i) agar_exp_tab_h[i]
+#define AGAR_ATAN_T(i, j) agar_atan_tab_h[i][j]
+#define AGAR_SINCOS_T(i) agar_sincos_tab_h[i]
+#endif
 
-/* (cos a, sin a) for a = atan2(dy, dx), without forming the angle.  atan2(0, 0) = 0 -> (1, 0). */
-AGAR_HD void agar_dir(double dy, double dx, double* c, double* s) {
-    double h2 = dx * dx + dy * dy;
-    if (h2 == 0.0) {
-        *c = 1.0;
-        *s = 0.0;
-        return;
+AGAR_HD double agar_pow(double x, double y) {
+    if (y == 0.0) return 1.0;
+    const uint64_t ix = agar_double_to_bits(x);
+    /* log_inline: x = 2^k z, z in [0x1.69555p-1, 0x1.69555p0), c = centre of z's subinterval */
+    const uint64_t tmp = ix - 0x3fe6955500000000ULL;
+    const int i = (int)((tmp >> 45) & 127);
+    const int k = (int)((int64_t)tmp >> 52);
+    const double z = agar_bits_to_double(ix - (tmp & 0xfff0000000000000ULL));
+    const double kd = (double)k;
+    const double invc = AGAR_POW_LOG_T(i, 0), logc = AGAR_POW_LOG_T(i, 1), logctail = AGAR_POW_LOG_T(i, 2);
+    const double r = fma(z, invc, -1.0);
+    const double t1 = fma(kd, AGAR_POW_LN2HI, logc);
+    const double lo1 = fma(kd, AGAR_POW_LN2LO, logctail);
+    const double t2 = t1 + r;
+    const double lo2 = (t1 - t2) + r;
+    const double ar = AGAR_POW_A0 * r;
+    const double ar2 = r * ar;
+    const double ar3 = r * ar2;
+    const double hi = t2 + ar2;
+    const double lo3 = fma(ar, r, -ar2);
+    const double lo4 = (t2 - hi) + ar2;
+    const double q = fma(ar2, fma(fma(r, AGAR_POW_A6, AGAR_POW_A5), ar2, fma(r, AGAR_POW_A4, AGAR_POW_A3)),
+                         fma(r, AGAR_POW_A2, AGAR_POW_A1));
+    const double lo = fma(ar3, q, ((lo1 + lo2) + lo3) + lo4);
+    const double lhi = hi + lo;
+    const double llo = (hi - lhi) + lo;
+    /* y * log x as ehi + elo */
+    const double ehi = y * lhi;
+    const double elo = fma(y, llo, fma(y, lhi, -ehi));
+    /* exp_inline(ehi, elo) */
+    const uint32_t abstop = (uint32_t)(agar_double_to_bits(ehi) >> 52) & 0x7ff;
+    if (abstop - 0x3c9u >= 0x3fu) {
+        if (abstop < 0x3c9u) return 1.0 + ehi;      /* |y log x| < 2^-54 */
+        return ehi > 0 ? (double)INFINITY : 0.0;     /* |y log x| >= 512: outside the path's domain */
     }
-    double h = sqrt(h2);
-    *c = dx / h;
-    *s = dy / h;
+    double kz = fma(ehi, AGAR_EXP_INVLN2N, AGAR_EXP_SHIFT);
+    const uint64_t ki = agar_double_to_bits(kz);
+    kz -= AGAR_EXP_SHIFT;
+    double rr = fma(kz, AGAR_EXP_NEGLN2HIN, ehi);
+    rr = fma(kz, AGAR_EXP_NEGLN2LON, rr);
+    rr = elo + rr;
+    const int idx = 2 * (int)(ki & 127);
+    const double tail = agar_bits_to_double(AGAR_EXP_T(idx));
+    const uint64_t sbits = AGAR_EXP_T(idx + 1) + (ki << 45);
+    const double r2 = rr * rr;
+    const double p23 = fma(rr, AGAR_EXP_C3, AGAR_EXP_C2);
+    const double p45 = fma(rr, AGAR_EXP_C5, AGAR_EXP_C4);
+    double t = fma(p23, r2, rr + tail);
+    t = fma(p45, r2 * r2, t);
+    const double scale = agar_bits_to_double(sbits);
+    return fma(t, scale, scale);
+}
+
+/* ---- atan2, sin, cos: BIT-IDENTICAL to glibc 2.39's FMA builds (what math.atan2 / math.cos / math.sin call on this image).
+ * e_atan2.c (IBM Accurate Mathematical Library): u = min(|y|,|x|) / max(|y|,|x|) with its division residual du; u < 1/16 ->
+ * odd polynomial to u^13, else the table cij[i] = {x_i, atan x_i, expansion of atan around x_i}; the octant decides how the
+ * result is assembled from pi/2 or pi as a double-double.  s_sin.c: |x| < 0.126 -> Taylor; else x = x_k + r with
+ * {sin x_k, cos x_k} from __sincostab (x_k ~ k/128) and short polynomials in r; 0.855 < |x| < 2.426 goes through pi/2 - |x|,
+ * larger arguments through the 4-part Cody-Waite reduction by pi/2.  Operation order and fma contractions follow the compiled
+ * code (disassembly of __atan2_fma / __sin_fma / __cos_fma), e.g. `s = x + x*xx*(sn3 + xx*sn5)` is ONE fma in do_cos.
+ * Domain: finite arguments; atan2 additionally |x|, |y| in {0} or [2^-500, 2^500] (no rescaling step, no subnormal results);
+ * sin / cos |x| < 105414350 (the path only passes angles in [-pi, pi]).  tests/test_portable_math.py: equal to libm on
+ * > 1e8 inputs each.  Reference call sites: cell.py:49-57,96-103 (atan2 -> cos, sin), field.py:363-366 (integer degrees). */
+#define AGAR_HPI 0x1.921fb54442d18p+0
+#define AGAR_HPI1 0x1.1a62633145c07p-54
+#define AGAR_OPI 0x1.921fb54442d18p+1
+#define AGAR_OPI1 0x1.1a62633145c07p-53
+
+AGAR_HD double agar_copysign(double mag, double sgn) {
+    return agar_bits_to_double((agar_double_to_bits(mag) & 0x7fffffffffffffffULL) | (agar_double_to_bits(sgn) & 0x8000000000000000ULL));
+}
+
+AGAR_HD double agar_atan2(double y, double x) {
+    const uint64_t bx = agar_double_to_bits(x), by = agar_double_to_bits(y);
+    const int xneg = (int)(bx >> 63);
+    if ((by << 1) == 0) { /* y = +-0: +-0 for x >= +0, +-pi otherwise */
+        if (!xneg) return y;
+        return (by >> 63) ? -AGAR_OPI : AGAR_OPI;
+    }
+    if (x == 0.0) return (by >> 63) ? -AGAR_HPI : AGAR_HPI;
+    double ax = fabs(x), ay = fabs(y);
+    const int de = (int)((uint32_t)(by >> 32) & 0x7ff00000u) - (int)((uint32_t)(bx >> 32) & 0x7ff00000u);
+    if (de >= 59768832) return y > 0 ? AGAR_HPI : -AGAR_HPI;      /* |y / x| > 2^57 */
+    if (de <= -59768832) {                                          /* |y / x| < 2^-57 */
+        if (x > 0) return agar_copysign(ay / ax, y);
+        return y > 0 ? AGAR_OPI : -AGAR_OPI;
+    }
+    double u, du;
+    if (ay < ax) {
+        u = ay / ax;
+        const double v = u * ax, vv = fma(u, ax, -v);
+        du = ((ay - v) - vv) / ax;
+    } else {
+        u = ax / ay;
+        const double v = u * ay, vv = fma(u, ay, -v);
+        du = ((ax - v) - vv) / ay;
+    }
+    double z;
+    const int small = u < 0.0625;
+    if (x > 0 && ay < ax) { /* (i) atan(ay / ax) */
+        if (small) {
+            const double v = u * u;
+            const double P = fma(v, fma(v, fma(v, fma(v, fma(v, 0x1.375f08b31cbcep-4, -0x1.7458022b13c25p-4), 0x1.c71c6e5129a3bp-4),
+                                               -0x1.24924923f7603p-3), 0x1.99999999997fdp-3), -0x1.5555555555555p-2);
+            z = u + fma(u * v, P, du);
+        } else {
+            const int i = (int)(fma(u, 256.0, 4503599627370496.0) - 4503599627370496.0) - 16;
+            const double t3 = u - AGAR_ATAN_T(i, 0);
+            const double v = du + t3;
+            const double dv = fabs(t3) > fabs(du) ? (t3 - v) + du : (du - v) + t3;
+            const double t2 = AGAR_ATAN_T(i, 2);
+            const double poly = fma(v, fma(v, fma(v, AGAR_ATAN_T(i, 6), AGAR_ATAN_T(i, 5)), AGAR_ATAN_T(i, 4)), AGAR_ATAN_T(i, 3));
+            z = fma(v, t2, fma(dv, t2, (v * v) * poly)) + AGAR_ATAN_T(i, 1);
+        }
+    } else {
+        /* (ii) x > 0: pi/2 - atan(ax/ay)   (iii) x < 0, ax < ay: pi/2 + atan(ax/ay)   (iv) x < 0: pi - atan(ay/ax);
+         * a subtraction is the addition of the exactly negated operand, so one code path serves all three */
+        const int iii = x < 0 && ax < ay;
+        const double K0 = (x > 0 || iii) ? AGAR_HPI : AGAR_OPI, K1 = (x > 0 || iii) ? AGAR_HPI1 : AGAR_OPI1;
+        if (small) {
+            const double v = u * u;
+            const double P = fma(v, fma(v, fma(v, fma(v, fma(v, 0x1.375f08b31cbcep-4, -0x1.7458022b13c25p-4), 0x1.c71c6e5129a3bp-4),
+                                               -0x1.24924923f7603p-3), 0x1.99999999997fdp-3), -0x1.5555555555555p-2);
+            const double zz = (u * v) * P;
+            const double su = iii ? u : -u, sdu = iii ? du : -du, szz = iii ? zz : -zz;
+            const double t2 = K0 + su;
+            const double cor = (K0 - t2) + su;
+            z = (((cor + K1) + sdu) + szz) + t2;
+        } else {
+            const int i = (int)(fma(u, 256.0, 4503599627370496.0) - 4503599627370496.0) - 16;
+            const double v = (u - AGAR_ATAN_T(i, 0)) + du;
+            const double q = fma(v, fma(v, fma(v, fma(v, AGAR_ATAN_T(i, 6), AGAR_ATAN_T(i, 5)), AGAR_ATAN_T(i, 4)), AGAR_ATAN_T(i, 3)),
+                                 AGAR_ATAN_T(i, 2));
+            const double c1 = AGAR_ATAN_T(i, 1);
+            z = (K0 + (iii ? c1 : -c1)) + fma(iii ? v : -v, q, K1);
+        }
+    }
+    return agar_copysign(z, y);
+}
+
+/* s_sin.c helpers; T = __sincostab */
+AGAR_HD double agar__taylor_sin(double a, double da) {
+    const double xx = a * a;
+    const double p = fma(xx, fma(xx, fma(xx, fma(xx, -0x1.addffc2fcdf59p-26, 0x1.71de27b9a7ed9p-19), -0x1.a01a019db08b8p-13),
+                                 0x1.1111111110ecep-7), -0x1.5555555555555p-3);
+    return a + fma(xx, fma(p, a, -(0.5 * da)), da);
+}
+AGAR_HD double agar__do_sin(double a, double da) {
+    const double dxs = a <= 0 ? -da : da, aa = fabs(a);
+    const double u = 0x1.8p45 + aa;
+    const double xr = aa - (u - 0x1.8p45);
+    const int k = (int)((uint32_t)agar_double_to_bits(u) << 2);
+    const double xx = xr * xr;
+    const double s = xr + fma(xr * xx, fma(xx, 0x1.11110e829872fp-7, -0x1.5555555555515p-3), dxs);
+    const double c = fma(xr, dxs, xx * fma(xx, fma(xx, 0x1.6c16bedd9e239p-10, -0x1.5555555555535p-5), 0.5));
+    const double sn = AGAR_SINCOS_T(k), ssn = AGAR_SINCOS_T(k + 1), cs = AGAR_SINCOS_T(k + 2), ccs = AGAR_SINCOS_T(k + 3);
+    const double cor = fma(s, cs, fma(-c, sn, fma(s, ccs, ssn)));
+    return agar_copysign(sn + cor, a);
+}
+AGAR_HD double agar__do_cos(double a, double da) {
+    const double dxs = a < 0 ? -da : da, aa = fabs(a);
+    const double u = 0x1.8p45 + aa;
+    const double xr = (aa - (u - 0x1.8p45)) + dxs;
+    const int k = (int)((uint32_t)agar_double_to_bits(u) << 2);
+    const double xx = xr * xr;
+    const double s = fma(xr * xx, fma(xx, 0x1.11110e829872fp-7, -0x1.5555555555515p-3), xr);
+    const double c = xx * fma(xx, fma(xx, 0x1.6c16bedd9e239p-10, -0x1.5555555555535p-5), 0.5);
+    const double sn = AGAR_SINCOS_T(k), ssn = AGAR_SINCOS_T(k + 1), cs = AGAR_SINCOS_T(k + 2), ccs = AGAR_SINCOS_T(k + 3);
+    const double cor = fma(-s, sn, fma(-c, cs, fma(-s, ssn, ccs)));
+    return cs + cor;
+}
+/* reduce_sincos: x = n pi/2 + (a + da), |a| <= pi/4; returns n mod 4 */
+AGAR_HD int agar__reduce_sincos(double x, double* a, double* da) {
+    const double t = fma(x, 0x1.45f306dc9c883p-1, 0x1.8p52);
+    const double xn = t - 0x1.8p52;
+    const int n = (int)(agar_double_to_bits(t) & 3);
+    const double y = fma(-xn, -0x1.dde973c000000p-27, fma(-xn, 0x1.921fb58000000p+0, x));
+    const double t2 = fma(-xn, -0x1.cb3b398000000p-55, y);
+    const double d0 = fma(-xn, -0x1.cb3b398000000p-55, y - t2);
+    const double b = fma(-xn, -0x1.d747f23e32ed7p-83, t2);
+    *a = b;
+    *da = d0 + fma(-xn, -0x1.d747f23e32ed7p-83, t2 - b);
+    return n;
+}
+AGAR_HD double agar__sin_small(double a, double da) { return fabs(a) < 0.126 ? agar__taylor_sin(a, da) : agar__do_sin(a, da); }
+
+AGAR_HD double agar_sin(double x) {
+    const uint32_t k = (uint32_t)(agar_double_to_bits(x) >> 32) & 0x7fffffffu;
+    if (k < 0x3e500000u) return x;
+    if (k < 0x3feb6000u) return agar__sin_small(x, 0.0);
+    if (k < 0x400368fdu) return agar_copysign(agar__do_cos(0x1.921fb54442d18p+0 - fabs(x), 0x1.1a62633145c07p-54), x);
+    double a, da;
+    const int n = agar__reduce_sincos(x, &a, &da);
+    const double r = (n & 1) ? agar__do_cos(a, da) : agar__sin_small(a, da);
+    return (n & 2) ? -r : r;
+}
+AGAR_HD double agar_cos(double x) {
+    const uint32_t k = (uint32_t)(agar_double_to_bits(x) >> 32) & 0x7fffffffu;
+    if (k < 0x3e400000u) return 1.0;
+    if (k < 0x3feb6000u) return agar__do_cos(x, 0.0);
+    if (k < 0x400368fdu) {
+        const double y = 0x1.921fb54442d18p+0 - fabs(x);
+        const double a = y + 0x1.1a62633145c07p-54;
+        return agar__sin_small(a, (y - a) + 0x1.1a62633145c07p-54);
+    }
+    double a, da;
+    const int n = agar__reduce_sincos(x, &a, &da) + 1;
+    const double r = (n & 1) ? agar__do_cos(a, da) : agar__sin_small(a, da);
+    return (n & 2) ? -r : r;
+}
+
+/* (cos a, sin a) for a = atan2(dy, dx) — cell.py:49-57: the angle is formed and rounded, then cos and sin are taken of it */
+AGAR_HD void agar_dir(double dy, double dx, double* c, double* s) {
+    const double a = agar_atan2(dy, dx);
+    *c = agar_cos(a);
+    *s = agar_sin(a);
 }
 
 /* Python's round(x, nd) for |x| * 10^nd < 2^51 (bot.py:16-20,449): the multiple of 10^-nd nearest to the

@@ -48,6 +48,12 @@ int agar_replay_sample_prioritized(AgarReplay* rp, const double* u_dev, int batc
                                    float* obs_t, float* action, float* reward, float* obs_tp1, uint8_t* done, void* stream);
 /* PrioritizedReplayBuffer.update_priorities (:173-195) */
 int agar_replay_update_priorities(AgarReplay* rp, const int32_t* idx_dev, const double* priorities_dev, int batch, void* stream);
+/* Sticky error bits raised ON THE DEVICE since create (synchronises `stream`).  Where the reference raises — sampling an empty
+ * buffer (random.randint(0, -1), replay_buffer.py:66; the prioritized path recurses without end for len < 2, :116) — or asserts
+ * (0 <= idx < len(storage), priority > 0, :203-204), the kernels skip the offending element (index 0 / weight 0 is returned,
+ * trees are left untouched) and set a bit here instead of hanging or corrupting memory. */
+enum { AGAR_RP_ERR_EMPTY = 1, AGAR_RP_ERR_INDEX = 2, AGAR_RP_ERR_PRIORITY = 4 };
+int agar_replay_error_flags(AgarReplay* rp, void* stream);
 /* number of kernels launched so far */
 int64_t agar_replay_launch_count(const AgarReplay* rp);
 

@@ -13,7 +13,8 @@
  *
  * Two builds (oracle/Makefile):
  *   libagar_oracle.so     libm transcendental functions, exactly as CPython calls them
- *   libagar_oracle_pm.so  -DAGAR_PORTABLE_MATH: include/agar_math.h (the arithmetic the CUDA kernels use)
+ *   libagar_oracle_pm.so  -DAGAR_PORTABLE_MATH: include/agar_math.h (the arithmetic the CUDA kernels use; since round 2 it is
+ *                         bit-identical to this image's libm, so the two builds give identical results)
  */
 #include <math.h>
 #include <stdint.h>
@@ -68,7 +69,7 @@ typedef struct OracleEnv {
 #ifdef AGAR_PORTABLE_MATH
 static inline void dir_of(double dy, double dx, double* c, double* s) { agar_dir(dy, dx, c, s); }
 static inline double m_pow(double x, double y) { return agar_pow(x, y); }
-static inline double m_sq(double x) { return x * x; }
+static inline double m_sq(double x) { return agar_pow(x, 2.0); } /* gsSize ** 2 == C pow(x, 2.0), bot.py:449 */
 static inline double round_dec(double x, int nd) { return agar_round_dec(x, nd == 5 ? 1e5 : 1e3); }
 #else
 /* cell.py:55-57 / 49-51: angle = math.atan2(yDiff, xDiff); math.cos(angle), math.sin(angle) */
@@ -1417,6 +1418,82 @@ uint64_t oracle_rollout_batch(const AgarConfig* cfg, int n_envs, uint64_t seed, 
 double oracle_pm_pow(double x, double y) { return agar_pow(x, y); }
 double oracle_pm_log(double x) { return agar_log(x); }
 double oracle_pm_exp(double x) { return agar_exp(x); }
+/* agar_pow against the C library's pow (what CPython's math.pow calls) on the path's domain: n pseudo-random inputs
+ * (radii, masses, a wide log-uniform band) x the exponents the path and the replay buffer use, plus every mass on a
+ * 1/64 grid up to the 22500 cap and its radius.  Returns the number of results whose BITS differ. */
+uint64_t oracle_pm_pow_mismatches(uint64_t n, uint64_t seed, double* first_x, double* first_y) {
+    static const double ys[8] = {0.475, -0.35, 0.32, 2.0, 0.6, -0.4, -1.0, 0.5};
+    uint64_t s = seed * 0x9E3779B97F4A7C15ULL + 88172645463325252ULL, bad = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+        double u = (double)(s >> 11) * (1.0 / 9007199254740992.0), x;
+        switch (i & 3) {
+            case 0: x = 0.5 + u * 90; break;
+            case 1: x = 1 + u * 22500; break;
+            case 2: x = exp((u - 0.5) * 40); break;
+            default: x = 4 + u * 200; break;
+        }
+        double y = ys[(i >> 2) & 7], a = agar_pow(x, y), b = pow(x, y);
+        if (memcmp(&a, &b, 8)) {
+            if (!bad && first_x) { *first_x = x; *first_y = y; }
+            ++bad;
+        }
+    }
+    for (int j = 64; j <= 22500 * 64; ++j) {
+        double m = j / 64.0, r = sqrt(m / M_PI);
+        double a = agar_pow(m, -0.35), b = pow(m, -0.35), c = agar_pow(r, 0.475), d = pow(r, 0.475);
+        if (memcmp(&a, &b, 8)) { if (!bad && first_x) { *first_x = m; *first_y = -0.35; } ++bad; }
+        if (memcmp(&c, &d, 8)) { if (!bad && first_x) { *first_x = r; *first_y = 0.475; } ++bad; }
+    }
+    return bad;
+}
+/* agar_atan2 / agar_sin / agar_cos against the C library on n pseudo-random inputs: direction vectors of every magnitude
+ * mix the game produces (field-scale, near-axis, tiny, integer lattice, near-diagonal, 35 decades log-uniform), and angles
+ * both uniform in [-pi, pi] and exactly as atan2 returns them.  Returns the number of results whose BITS differ. */
+uint64_t oracle_pm_trig_mismatches(uint64_t n, uint64_t seed) {
+    uint64_t s = seed * 0x9E3779B97F4A7C15ULL + 88172645463325252ULL, bad = 0;
+#define U01() (s ^= s << 13, s ^= s >> 7, s ^= s << 17, (double)(s >> 11) * (1.0 / 9007199254740992.0))
+    for (uint64_t i = 0; i < n; ++i) {
+        double x, y;
+        switch (i & 7) {
+            case 0: x = (U01() - 0.5) * 600; y = (U01() - 0.5) * 600; break;
+            case 1: x = (U01() - 0.5) * 2; y = (U01() - 0.5) * 600; break;
+            case 2: x = (U01() - 0.5) * 600; y = (U01() - 0.5) * 2; break;
+            case 3: x = (U01() - 0.5) * 1e-6; y = (U01() - 0.5) * 100; break;
+            case 4: x = (U01() - 0.5) * 100; y = (U01() - 0.5) * 1e-9; break;
+            case 5: x = floor((U01() - 0.5) * 100); y = floor((U01() - 0.5) * 100); break;
+            case 6: {
+                double m0 = exp((U01() - 0.5) * 80), s0 = U01(), m1 = exp((U01() - 0.5) * 80), s1 = U01();
+                x = s0 < 0.5 ? -m0 : m0;
+                y = s1 < 0.5 ? -m1 : m1;
+                break;
+            }
+            default: {
+                x = (U01() - 0.5) * 20;
+                double f = U01(), g = U01();
+                y = x * (1 + (f - 0.5) * 0.2);
+                if (g < 0.5) y = -y;
+                break;
+            }
+        }
+        double a = agar_atan2(y, x), b = atan2(y, x);
+        bad += memcmp(&a, &b, 8) != 0;
+        double ang = (i & 8) ? b : (U01() - 0.5) * 2 * M_PI;
+        double s1 = agar_sin(ang), s2 = sin(ang), c1 = agar_cos(ang), c2 = cos(ang);
+        bad += memcmp(&s1, &s2, 8) != 0;
+        bad += memcmp(&c1, &c2, 8) != 0;
+    }
+#undef U01
+    for (int yy = -300; yy <= 300; ++yy) /* fresh cells and pellets sit on integer coordinates */
+        for (int xx = -300; xx <= 300; ++xx) {
+            double a = agar_atan2(yy, xx), b = atan2(yy, xx);
+            bad += memcmp(&a, &b, 8) != 0;
+        }
+    return bad;
+}
+double oracle_pm_atan2(double y, double x) { return agar_atan2(y, x); }
+double oracle_pm_sin(double x) { return agar_sin(x); }
+double oracle_pm_cos(double x) { return agar_cos(x); }
 void oracle_pm_dir(double dy, double dx, double* c, double* s) { agar_dir(dy, dx, c, s); }
 double oracle_pm_round_dec(double x, double scale) { return agar_round_dec(x, scale); }
 /* spatialHashTable.py:70-83 for one axis, exported for the closed-form pellet-rectangle proof in tests */

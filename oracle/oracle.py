@@ -23,7 +23,7 @@ def build(force=False):
     """Compile both oracle builds with the committed Makefile (gcc only)."""
     targets = [os.path.join(_HERE, n) for n in ("libagar_oracle.so", "libagar_oracle_pm.so")]
     src = os.path.join(_HERE, "agar_oracle.c")
-    deps = [src] + [os.path.join(_ROOT, "include", n) for n in ("agar_b200.h", "agar_layout.h", "agar_math.h")]
+    deps = [src] + [os.path.join(_ROOT, "include", n) for n in ("agar_b200.h", "agar_layout.h", "agar_math.h", "agar_libm_tables.h")]
     stale = force or any(not os.path.exists(t) or any(os.path.getmtime(t) < os.path.getmtime(d) for d in deps)
                          for t in targets)
     if stale:
@@ -57,6 +57,15 @@ def load(portable=False):
     lib.oracle_field_update.argtypes = [vp]
     lib.oracle_pm_pow.argtypes = [ctypes.c_double, ctypes.c_double]
     lib.oracle_pm_pow.restype = ctypes.c_double
+    lib.oracle_pm_pow_mismatches.argtypes = [u64, u64, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+    lib.oracle_pm_pow_mismatches.restype = u64
+    lib.oracle_pm_trig_mismatches.argtypes = [u64, u64]
+    lib.oracle_pm_trig_mismatches.restype = u64
+    for name in ("oracle_pm_sin", "oracle_pm_cos"):
+        getattr(lib, name).argtypes = [ctypes.c_double]
+        getattr(lib, name).restype = ctypes.c_double
+    lib.oracle_pm_atan2.argtypes = [ctypes.c_double, ctypes.c_double]
+    lib.oracle_pm_atan2.restype = ctypes.c_double
     lib.oracle_pm_log.argtypes = [ctypes.c_double]
     lib.oracle_pm_log.restype = ctypes.c_double
     lib.oracle_pm_exp.argtypes = [ctypes.c_double]

@@ -21,7 +21,8 @@ def records(batch):
     return [lay.Record(batch.layout, st[i].copy()) for i in range(batch.n_envs)]
 
 
-def check(which="1", n_envs=32, frames=200, seed=3, first_env=5, tile_width=None, every=1, event_cap=64, verbose=True):
+def check(which="1", n_envs=32, frames=200, seed=3, first_env=5, tile_width=None, every=1, event_cap=64, verbose=True, tally=None):
+    """tally: dict that receives the event-type counts of the ORACLE's per-frame event logs (all envs, all frames)."""
     cfg = lay.derive_config(event_cap=event_cap, **(which if isinstance(which, dict) else KWS[which]))
     batch = AgarBatch(cfg, n_envs, seed=seed, first_env_id=first_env, tile_width=tile_width)
     L = batch.layout
@@ -65,6 +66,12 @@ def check(which="1", n_envs=32, frames=200, seed=3, first_env=5, tile_width=None
                         bad.append("frame %d env %d agent %d obs[%d]: gpu %r oracle %r (%d bad)" % (
                             t, i, a, j, obs[i, a, j], tr[a]["obs32"][j], int(neq.sum())))
             oras[i].step(act[i], 1)
+            if tally is not None:
+                rec = oras[i].record
+                n = min(int(rec.header["n_events"][0]), L.event_cap)
+                if n:
+                    for typ, cnt in zip(*np.unique(rec.events["type"][:n], return_counts=True)):
+                        tally[lay.EV_NAMES[int(typ)]] = tally.get(lay.EV_NAMES[int(typ)], 0) + int(cnt)
         batch.step(act, 1)
         if bad or ((t + 1) % every == 0 and not cmp("frame %d" % t)):
             print("\n".join(bad[:30])); return False
