@@ -176,6 +176,7 @@ k_main(const __grid_constant__ DevParams P, uint8_t* __restrict__ state, const f
         __syncthreads();
         pel_cache_copy(P, state, env0, n_here, tiles, false);
     }
+    export_tail(P, obs, env0, n_here);
 }
 
 
@@ -263,6 +264,7 @@ k_simple(const __grid_constant__ DevParams P, const SimplePlan SP, uint8_t* __re
         uint32_t* dst = (uint32_t*)(state + (size_t)(env0 + e) * P.L.record_bytes) + pel_word;
         dst[w] = *(const uint32_t*)(g_smem + (size_t)e * SP.strideB + w * 4);
     }
+    export_tail(P, obs, env0, n_here);
 }
 
 /* mode 0: Model(...) + createBot*K + Model.initialize (model.py:51,154-162,90-94; field.py:57-67)
@@ -340,21 +342,6 @@ k_init(const __grid_constant__ DevParams P, uint8_t* __restrict__ state, const u
     }
 }
 
-/* agar_step_host with pinned (device-visible) caller buffers: observations and the packed reward | done words leave
- * through the SMs' own stores over PCIe, so no copy-engine operation (and none of its start latency) sits between the
- * step kernel and the host.  n16 / n4: 16-byte and trailing 4-byte units of the observation block. */
-__global__ void k_export(const uint4* __restrict__ obs, uint4* __restrict__ obs_host, size_t n16, size_t n4_tail,
-                         const uint32_t* __restrict__ turn, uint32_t* __restrict__ turn_host, size_t n4_turn) {
-    const size_t stride = (size_t)gridDim.x * blockDim.x, i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (obs_host) {
-        for (size_t i = i0; i < n16; i += stride) obs_host[i] = obs[i];
-        const uint32_t* t = (const uint32_t*)(obs + n16);
-        uint32_t* th = (uint32_t*)(obs_host + n16);
-        for (size_t i = i0; i < n4_tail; i += stride) th[i] = t[i];
-    }
-    for (size_t i = i0; i < n4_turn; i += stride) turn_host[i] = turn[i];
-}
-
 /* agar_get: one thread per (env, agent) or per env, straight from HBM */
 __global__ void k_get(const __grid_constant__ DevParams P, const uint8_t* __restrict__ state, int which, void* out) {
     const int A = P.L.n_agents;
@@ -409,7 +396,11 @@ struct AgarEnv {
     /* step_host staging */
     float *d_actions, *d_obs, *d_reward;
     uint8_t* d_done;
-    void* h_turn; /* pinned */
+    void* h_turn; /* pinned: float reward[EA] | uint8 done[EA], then (64-byte aligned) the completion flag word */
+    volatile uint32_t* h_flag; /* inside h_turn's allocation; the last CTA of a zero-copy step launch writes flag_seq there */
+    unsigned int* d_export_count;
+    uint32_t flag_seq;
+    int host_polling; /* the pending step raises h_flag (zero-copy path) */
     int host_pending; /* agar_step_host_begin issued, _end not yet */
     int host_zerocopy; /* pinned caller buffers are read / written in place (AGAR_HOST_ZEROCOPY=0 disables) */
 };
@@ -571,7 +562,7 @@ extern "C" int agar_set_tile_width(AgarEnv* e, int W) {
         int tail_words = (int)((e->L.record_bytes - e->L.off_pellets) / 4);
         e->sp.strideB = (tail_words | 1) * 4;
         if (e->L.pellet_cap > 128 * W) return fail(e, AGAR_E_UNSUPPORTED, "pellet pool too large for this tile width%s", "");
-        int threads = e->n_envs >= 262144 ? 128 : 64; /* measured: two warps per CTA below ~256k envs, four above */
+        int threads = 128; /* measured (round 2, exact libm arithmetic): four warps per CTA beat two at every batch size (4096 envs: 7.7e8 vs 7.0e8) */
         const char* tenv = getenv("AGAR_SIMPLE_THREADS");
         if (tenv && atoi(tenv) >= 32) threads = atoi(tenv) / 32 * 32;
         if (threads > 256) threads = 256; /* __launch_bounds__(256, ...) */
@@ -702,6 +693,7 @@ extern "C" int agar_destroy(AgarEnv* e) {
     if (e->d_obs) cudaFree(e->d_obs);
     if (e->d_reward) cudaFree(e->d_reward);
     if (e->h_turn) cudaFreeHost(e->h_turn);
+    if (e->d_export_count) cudaFree(e->d_export_count);
     free(e);
     return AGAR_OK;
 }
@@ -796,7 +788,13 @@ extern "C" int agar_step_host_begin(AgarEnv* e, const float* actions_host, int n
         CU(cudaMalloc(&e->d_actions, EA * 4 * sizeof(float)));
         CU(cudaMalloc(&e->d_obs, EA * e->L.state_len * sizeof(float)));
         CU(cudaMalloc(&e->d_reward, turn_words * 4)); /* packed: float reward[EA] | uint8 done[EA] -> one copy back */
-        CU(cudaMallocHost(&e->h_turn, turn_words * 4));
+        const size_t flag_off = (turn_words * 4 + 63) / 64 * 64;
+        CU(cudaMallocHost(&e->h_turn, flag_off + 64));
+        e->h_flag = (volatile uint32_t*)((uint8_t*)e->h_turn + flag_off);
+        *e->h_flag = 0;
+        e->flag_seq = 0;
+        CU(cudaMalloc(&e->d_export_count, sizeof(unsigned int)));
+        CU(cudaMemsetAsync(e->d_export_count, 0, sizeof(unsigned int), s));
         e->d_done = (uint8_t*)e->d_reward + EA * 4;
         CU(cudaMemsetAsync(e->d_obs, 0, EA * e->L.state_len * sizeof(float), s));
         CU(cudaMemsetAsync(e->d_reward, 0, turn_words * 4, s));
@@ -804,26 +802,34 @@ extern "C" int agar_step_host_begin(AgarEnv* e, const float* actions_host, int n
         e->host_zerocopy = zc ? atoi(zc) : 1;
     }
     /* Pinned caller buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory) are visible to the device: the step
-     * kernel reads the actions in place and k_export stores the results straight into them.  Pageable buffers take the
+     * kernel reads the actions in place and its CTAs store the results straight into them (export_tail).  Pageable buffers take the
      * copy-engine path. */
     const float* act_dev = e->host_zerocopy ? (const float*)pinned_dev_ptr(actions_host) : nullptr;
     float* obs_dev_host = (e->host_zerocopy && obs_host) ? (float*)pinned_dev_ptr(obs_host) : nullptr;
     const bool zero_copy = act_dev && (!obs_host || (obs_dev_host && ((uintptr_t)obs_dev_host & 15) == 0));
     if (!zero_copy) CU(cudaMemcpyAsync(e->d_actions, actions_host, EA * 4 * sizeof(float), cudaMemcpyHostToDevice, s));
     e->P.turn_reward = e->d_reward, e->P.turn_done = e->d_done; /* reward / done written by the step kernel itself */
+    e->host_polling = 0;
+    if (zero_copy) { /* ONE launch: each CTA exports its own rows over PCIe and the last one raises the flag (export_tail) */
+        void* turn_dev_host = nullptr;
+        void* flag_dev_host = nullptr;
+        CU(cudaHostGetDevicePointer(&turn_dev_host, e->h_turn, 0));
+        CU(cudaHostGetDevicePointer(&flag_dev_host, (void*)e->h_flag, 0));
+        e->flag_seq += 1;
+        if (e->flag_seq == 0) e->flag_seq = 1;
+        e->P.host_obs = obs_dev_host, e->P.host_turn = (uint32_t*)turn_dev_host, e->P.export_count = e->d_export_count;
+        e->P.host_flag = (volatile uint32_t*)flag_dev_host, e->P.flag_value = e->flag_seq;
+        e->host_polling = 1;
+    }
     int rc = launch_main(e, zero_copy ? act_dev : e->d_actions, e->d_obs, n_frames, 1, KF_OBS_AFTER, 0, s);
     e->P.turn_reward = nullptr, e->P.turn_done = nullptr;
-    if (rc != AGAR_OK) return rc;
-    const size_t obs_bytes = EA * e->L.state_len * sizeof(float);
-    if (zero_copy) {
-        void* turn_dev_host = nullptr;
-        CU(cudaHostGetDevicePointer(&turn_dev_host, e->h_turn, 0));
-        k_export<<<296, 256, 0, s>>>((const uint4*)e->d_obs, (uint4*)obs_dev_host, obs_bytes / 16, (obs_bytes % 16) / 4,
-                                     (const uint32_t*)e->d_reward, (uint32_t*)turn_dev_host, turn_words);
-        cudaError_t err = cudaGetLastError();
-        if (err != cudaSuccess) return fail(e, AGAR_E_CUDA, "kernel launch failed: %s", cudaGetErrorString(err));
-        e->launches += 1;
-    } else {
+    e->P.host_obs = nullptr, e->P.host_turn = nullptr, e->P.export_count = nullptr, e->P.host_flag = nullptr;
+    if (rc != AGAR_OK) {
+        e->host_polling = 0;
+        return rc;
+    }
+    if (!zero_copy) {
+        const size_t obs_bytes = EA * e->L.state_len * sizeof(float);
         if (obs_host) CU(cudaMemcpyAsync(obs_host, e->d_obs, obs_bytes, cudaMemcpyDeviceToHost, s));
         CU(cudaMemcpyAsync(e->h_turn, e->d_reward, EA * 5, cudaMemcpyDeviceToHost, s));
     }
@@ -836,7 +842,26 @@ extern "C" int agar_step_host_end(AgarEnv* e, float* reward_host, uint8_t* done_
     if (!e) return AGAR_E_INVALID;
     if (!e->host_pending) return fail(env, AGAR_E_INVALID, "%s", "agar_step_host_end without agar_step_host_begin");
     CU(cudaSetDevice(e->device));
-    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    if (e->host_polling) {
+        /* the launch's last CTA writes flag_seq into pinned memory after every row has been made visible system-wide: poll it
+         * (a few hundred ns of latency instead of a driver wake-up); cudaStreamQuery now and then catches a failed launch */
+        const uint32_t want = e->flag_seq;
+        unsigned spins = 0;
+        while (*e->h_flag != want) {
+            if ((++spins & 0xfff) == 0) {
+                cudaError_t q = cudaStreamQuery((cudaStream_t)stream);
+                if (q == cudaSuccess) break;
+                if (q != cudaErrorNotReady) return fail(env, AGAR_E_CUDA, "CUDA error: %s", cudaGetErrorString(q));
+            }
+#if defined(__x86_64__) || defined(__i386__)
+            __builtin_ia32_pause();
+#endif
+        }
+        if (*e->h_flag != want) CU(cudaStreamSynchronize((cudaStream_t)stream)); /* the stream drained without the flag: surface the error */
+        e->host_polling = 0;
+    } else {
+        CU(cudaStreamSynchronize((cudaStream_t)stream));
+    }
     e->host_pending = 0;
     const size_t EA = (size_t)e->n_envs * (e->L.n_agents ? e->L.n_agents : 1);
     if (reward_host) memcpy(reward_host, e->h_turn, EA * 4);

@@ -48,6 +48,13 @@ struct DevParams {
     /* optional per-launch outputs of the last bot turn ([E][A]); NULL = use agar_get */
     float* turn_reward;
     uint8_t* turn_done;
+    /* agar_step_host with pinned caller buffers: every CTA of the step launch exports its own envs' rows over PCIe as soon as
+     * it has finished them (export_tail below); the last CTA raises a flag in host memory the caller polls */
+    float* host_obs;             /* device-visible address of the caller's pinned observation buffer, or NULL           */
+    uint32_t* host_turn;         /* device-visible address of the pinned packed block: float reward[EA] | uint8 done[EA] */
+    unsigned int* export_count;  /* device counter of CTAs that have exported                                          */
+    volatile uint32_t* host_flag;
+    uint32_t flag_value;
 };
 
 /* flags of k_main */
@@ -75,6 +82,46 @@ struct Ctx {
 };
 
 #define CELLP(c, P, k, i) (&(c).cells[(k) * (P).L.cell_cap + (i)])
+
+/* Tail of a step launch issued by agar_step_host (every thread of the CTA calls it): the observation rows and the reward /
+ * done words of this CTA's envs [env0, env0 + n_here) go from the device staging buffers (just written by this CTA's own
+ * threads; read back through L2, where the observation REDs landed) to the caller's pinned buffers with 16-byte stores.
+ * No second kernel, no grid-wide wait: a CTA's rows leave while other CTAs still step.  __threadfence_system orders the
+ * PCIe writes before the CTA's count; the CTA that counts last writes the flag the host polls. */
+__device__ __forceinline__ void export_tail(const DevParams& P, const float* obs_dev, int env0, int n_here) {
+    if (!P.host_turn) return;
+    __syncthreads();
+    const int A = P.L.n_agents > 0 ? P.L.n_agents : 1;
+    const size_t tid = threadIdx.x, nt = blockDim.x;
+    if (P.host_obs && obs_dev) {
+        const size_t w0 = (size_t)env0 * A * P.L.state_len, w1 = w0 + (size_t)n_here * A * P.L.state_len; /* float indices */
+        size_t a0 = (w0 + 3) & ~(size_t)3;
+        if (a0 > w1) a0 = w1;
+        const size_t a1 = a0 + ((w1 - a0) & ~(size_t)3);
+        for (size_t i = w0 + tid; i < a0; i += nt) P.host_obs[i] = __ldcg(obs_dev + i);
+        for (size_t i = a0 / 4 + tid; i < a1 / 4; i += nt) ((uint4*)P.host_obs)[i] = __ldcg((const uint4*)obs_dev + i);
+        for (size_t i = a1 + tid; i < w1; i += nt) P.host_obs[i] = __ldcg(obs_dev + i);
+    }
+    {
+        const size_t EA = (size_t)P.n_envs * A, t0 = (size_t)env0 * A, t1 = t0 + (size_t)n_here * A;
+        float* hr = (float*)P.host_turn;
+        uint8_t* hd = (uint8_t*)P.host_turn + EA * 4;
+        for (size_t i = t0 + tid; i < t1; i += nt) {
+            hr[i] = __ldcg(P.turn_reward + i);
+            hd[i] = __ldcg(P.turn_done + i);
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int c = atomicAdd(P.export_count, 1u);
+        if (c == gridDim.x - 1) {
+            *P.export_count = 0; /* every other CTA has counted: ready for the next launch */
+            __threadfence_system();
+            *P.host_flag = P.flag_value;
+        }
+    }
+}
 
 /* ------------------------------------------------------------------ small exact helpers */
 DEV double py_max0(double v) { return v > 0 ? v : 0.0; }

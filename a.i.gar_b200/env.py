@@ -74,7 +74,9 @@ _GET_DTYPES = {lay.GET_REWARD: "float32", lay.GET_DONE: "uint8", lay.GET_VALID: 
 class AgarBatch(object):
     """E lock-stepped agar.io envs on one GPU.  All device work is enqueued on torch's current stream."""
 
-    def __init__(self, cfg, n_envs, device=0, seed=0, first_env_id=0, tile_width=None):
+    def __init__(self, cfg, n_envs, device=0, seed=0, first_env_id=0, tile_width=None, stream=None):
+        """stream: a torch.cuda.Stream every call of this handle is enqueued on (default: torch's current stream at call time).
+        Several handles on their own streams step concurrently — the env groups of a host-side pipeline (step_host_begin / _end)."""
         import torch
         if not torch.cuda.is_available():
             raise AgarError("no CUDA device: the agar.io step has no CPU fallback")
@@ -83,6 +85,7 @@ class AgarBatch(object):
         self.cfg = cfg
         self.n_envs = int(n_envs)
         self.device = torch.device("cuda", device)
+        self.stream = stream
         self.h = ctypes.c_void_p()
         with torch.cuda.device(self.device):
             rc = self.lib.agar_create(ctypes.byref(cfg), self.n_envs, self.device.index, seed, first_env_id,
@@ -100,6 +103,8 @@ class AgarBatch(object):
 
     # ---- plumbing
     def _stream(self):
+        if self.stream is not None:
+            return ctypes.c_void_p(self.stream.cuda_stream)
         return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
 
     def _check(self, rc):
@@ -203,6 +208,20 @@ class AgarBatch(object):
     def step_host_end(self, reward_out, done_out):
         self._check(self.lib.agar_step_host_end(self.h, reward_out.ctypes.data, done_out.ctypes.data, self._stream()))
         self._pending = None
+
+    # the same two calls on raw host addresses (ints), for loops that reuse pinned buffers and do not want numpy's
+    # ctypes conversion on every call; the caller keeps the buffers alive
+    def step_host_begin_ptr(self, actions_addr, n_frames, obs_addr):
+        rc = self.lib.agar_step_host_begin(self.h, actions_addr, n_frames, obs_addr,
+                                           self.stream.cuda_stream if self.stream is not None else self._stream())
+        if rc != 0:
+            self._check(rc)
+
+    def step_host_end_ptr(self, reward_addr, done_addr):
+        rc = self.lib.agar_step_host_end(self.h, reward_addr, done_addr,
+                                         self.stream.cuda_stream if self.stream is not None else self._stream())
+        if rc != 0:
+            self._check(rc)
 
     # ---- parity / debugging
     def dump(self, env_index):

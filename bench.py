@@ -171,6 +171,98 @@ def workload_name(envs, frames):
             "random-action driver, %d-frame rollouts (frame-skip 7, obs every 8th frame)" % (envs, frames))
 
 
+def run_e2e(cfg, E, decisions, e2e_steps, local, rank, world, dist, barrier, groups, seed=2026):
+    """The same rollout driven from the HOST through the public C ABI: every decision the caller's pinned action buffer goes
+    in and its pinned observation / reward / done buffers come back (agar_step_host_begin / _end, include/agar_b200.h).
+    The envs are split into `groups` handles on their own streams, exactly as a CPU policy would pipeline them: while one
+    group steps on the GPU the host already holds the previous group's observations.  Every group still receives the
+    observation of decision d before its action of decision d + 1 is submitted.  Copies are inside the timed region: the
+    step kernel reads the actions in place over PCIe and its CTAs store their rows into the caller's buffers."""
+    import torch
+    import aigar_b200.layout as lay
+    from aigar_b200.env import AgarBatch
+    G = max(1, min(groups, E))
+    Eg = E // G
+    assert Eg * G == E, "--groups must divide --envs"
+    device = torch.device("cuda", local)
+    streams = [torch.cuda.Stream(device=device) for _ in range(G)]
+    hs = [AgarBatch(cfg, Eg, device=local, seed=seed, first_env_id=rank * E + g * Eg, stream=streams[g]) for g in range(G)]
+    L = hs[0].layout
+    A = max(L.n_agents, 1)
+    acts = torch.rand((decisions, E, A, 4), dtype=torch.float32).pin_memory()
+    obs_h = torch.empty((E, A, L.state_len), dtype=torch.float32).pin_memory()
+    rew_h = torch.empty((E, A), dtype=torch.float32).pin_memory()
+    done_h = torch.empty((E, A), dtype=torch.uint8).pin_memory()
+    # raw addresses of every (decision, group) slice: no per-call numpy / ctypes conversion inside the timed loop
+    a_ptr = [[acts[d, g * Eg:(g + 1) * Eg].data_ptr() for g in range(G)] for d in range(decisions)]
+    o_ptr = [obs_h[g * Eg:(g + 1) * Eg].data_ptr() for g in range(G)]
+    r_ptr = [rew_h[g * Eg:(g + 1) * Eg].data_ptr() for g in range(G)]
+    d_ptr = [done_h[g * Eg:(g + 1) * Eg].data_ptr() for g in range(G)]
+
+    clock = time.perf_counter
+    last_launch = [0.0]
+
+    def begin(g, d, spacing):
+        # pacing: consecutive launches at least `spacing` apart, so that the groups run out of phase — one group's PCIe export
+        # overlaps the other's frames (groups launched together finish together and the GPU idles while the rows leave)
+        if spacing > 0.0:
+            while clock() - last_launch[0] < spacing:
+                pass
+        hs[g].step_host_begin_ptr(a_ptr[d][g], PERIOD, o_ptr[g])
+        last_launch[0] = clock()
+
+    def rollout(spacing, n_dec=decisions):
+        for g in range(G):
+            begin(g, 0, spacing)
+        for d in range(1, n_dec):
+            for g in range(G):
+                hs[g].step_host_end_ptr(r_ptr[g], d_ptr[g])      # observation / reward / done of decision d - 1 are on the host
+                begin(g, d, spacing)
+        for g in range(G):
+            hs[g].step_host_end_ptr(r_ptr[g], d_ptr[g])
+
+    for g in range(G):
+        hs[g].observe()
+    rollout(0.0)  # warm-up: one full rollout
+    spacing = 0.0
+    if G > 1:  # pick the launch spacing in the warm-up: fractions of the unpaced per-decision time
+        n_try = min(decisions, 40)
+        torch.cuda.synchronize()
+        t0 = clock()
+        rollout(0.0, n_try)
+        base = (clock() - t0) / n_try
+        best = base
+        for frac in (0.15, 0.25, 0.35, 0.45, 0.55):
+            cand = base * frac * 2.0 / G
+            t0 = clock()
+            rollout(cand, n_try)
+            t = (clock() - t0) / n_try
+            if t < best:
+                best, spacing = t, cand
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        rollout(spacing)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device=device)
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt = float(tt.item())
+    launches = sum(h.launch_count for h in hs)
+    for h in hs:
+        h.close()
+    frames = decisions * PERIOD
+    return {"value": world * E * frames * e2e_steps / dt, "unit": UNIT,
+            "h2d_bytes_per_step": int(decisions * acts[0].numel() * 4),
+            "d2h_bytes_per_step": int(decisions * (obs_h.numel() * 4 + rew_h.numel() * 4 + done_h.numel())),
+            "steps": e2e_steps, "calls_per_step": decisions * G, "groups": G, "launch_spacing_us": spacing * 1e6,
+            "ms_per_step": dt / e2e_steps * 1e3,
+            "api": "agar_step_host_begin / agar_step_host_end (C ABI, pinned host buffers; %d env groups of %d on their own "
+                   "streams: actions read in place by the step kernel, its CTAs store obs / reward / done over PCIe and raise "
+                   "a flag the host polls; one launch per call)" % (G, Eg)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -180,6 +272,7 @@ def main():
     ap.add_argument("--envs", type=int, default=4096)
     ap.add_argument("--frames", type=int, default=1000)
     ap.add_argument("--tile", type=int, default=0)
+    ap.add_argument("--groups", type=int, default=4, help="env groups in flight on the host-buffer (e2e) path")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
@@ -246,33 +339,10 @@ def main():
     total_ms = float(t.item())
     value = world * E * frames * args.steps / (total_ms * 1e-3)
 
-    # ---- e2e: host buffers through agar_step_host (actions H2D, obs/reward/done D2H every decision)
+    # ---- e2e: host buffers through the C ABI's host-buffer step (actions H2D, obs/reward/done D2H every decision)
     e2e = None
     if not args.no_e2e:
-        A = max(L.n_agents, 1)
-        acts = torch.rand((decisions, E, A, 4), dtype=torch.float32).pin_memory().numpy()
-        obs_h = torch.empty((E, A, L.state_len), dtype=torch.float32).pin_memory().numpy()
-        rew_h = torch.empty((E, A), dtype=torch.float32).pin_memory().numpy()
-        done_h = torch.empty((E, A), dtype=torch.uint8).pin_memory().numpy()
-        e2e_steps = min(args.steps, 5)
-        for d in range(min(decisions, 16)):
-            batch.step_host(acts[d], PERIOD, obs_h, rew_h, done_h)
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(e2e_steps):
-            for d in range(decisions):
-                batch.step_host(acts[d], PERIOD, obs_h, rew_h, done_h)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=batch.device)
-        if dist is not None:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-        e2e = {"value": world * E * frames * e2e_steps / dt, "unit": UNIT,
-               "h2d_bytes_per_step": int(decisions * acts[0].nbytes),
-               "d2h_bytes_per_step": int(decisions * (obs_h.nbytes + rew_h.nbytes + done_h.nbytes)),
-               "steps": e2e_steps, "calls_per_step": decisions, "api": "agar_step_host (C ABI, pinned host buffers: actions read in place by the step kernel, obs/reward/done stored over PCIe by k_export)"}
-
+        e2e = run_e2e(cfg, E, decisions, min(args.steps, 5), local, rank, world, dist, barrier, args.groups)
     # ---- episode statistics: the one optional collective, outside the timed region
     stats = batch.get(lay.GET_STATS).sum(dim=(0, 1))
     ovf = (batch.get(lay.GET_OVERFLOW) != 0).sum().to(torch.float64)

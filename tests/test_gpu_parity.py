@@ -194,6 +194,44 @@ def test_host_buffer_path(torch_cuda):
     assert a.launch_count > 0
 
 
+@pytest.mark.parametrize("kw,n", [(dict(), 64), (dict(num_nn=1, num_greedy=1, virus=True, split=True, eject=True), 24),
+                                  (dict(num_nn=2, num_greedy=1, virus=True, split=True, eject=True), 10)])
+def test_host_buffer_path_pinned_groups(torch_cuda, kw, n):
+    """The e2e path as bench.py drives it: PINNED caller buffers (the step kernel reads the actions in place, its CTAs store
+    observations / reward / done straight into the caller's memory and raise the flag agar_step_host_end polls — one launch
+    per call, no export kernel), two env groups on their own streams via _begin / _end.  Equal to one big device-buffer batch."""
+    torch = torch_cuda
+    cfg = lay.derive_config(**kw)
+    ref = _batch(cfg, n, seed=21, first_env_id=7)
+    G, ng = 2, n // 2
+    streams = [torch.cuda.Stream() for _ in range(G)]
+    from aigar_b200.env import AgarBatch
+    hs = [AgarBatch(cfg, ng, seed=21, first_env_id=7 + g * ng, stream=streams[g]) for g in range(G)]
+    L = ref.layout
+    A = max(L.n_agents, 1)
+    acts = torch.rand((14, n, A, 4), dtype=torch.float32).pin_memory()
+    obs_h = torch.zeros((n, A, L.state_len), dtype=torch.float32).pin_memory()
+    rew_h = torch.zeros((n, A), dtype=torch.float32).pin_memory()
+    done_h = torch.zeros((n, A), dtype=torch.uint8).pin_memory()
+    ref.observe()
+    for h in hs:
+        h.observe()
+    launches0 = sum(h.launch_count for h in hs)
+    for t in range(14):
+        for g in range(G):
+            sl = slice(g * ng, (g + 1) * ng)
+            hs[g].step_host_begin(acts[t, sl].numpy(), 8, obs_h[sl].numpy())
+        o = ref.step_observe(acts[t].cuda(), 8)
+        for g in range(G):
+            sl = slice(g * ng, (g + 1) * ng)
+            hs[g].step_host_end(rew_h[sl].numpy(), done_h[sl].numpy())
+        assert np.array_equal(obs_h.numpy(), o.cpu().numpy()), t
+        assert np.array_equal(rew_h.numpy(), ref.get(lay.GET_REWARD).cpu().numpy()), t
+        assert np.array_equal(done_h.numpy(), ref.get(lay.GET_DONE).cpu().numpy()), t
+    assert sum(h.launch_count for h in hs) - launches0 == 14 * G  # ONE kernel per host-buffer call
+    assert torch.equal(torch.cat([h.state_tensor() for h in hs]), ref.state_tensor())
+
+
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
 def test_gpu_against_reference_golden(torch_cuda, path):
     """The CUDA path replays what the REFERENCE was fed (tests/golden, generated by executing the unpatched reference):
@@ -244,9 +282,12 @@ def test_long_reference_fixtures_cover_every_event_type():
 
 
 @pytest.mark.parametrize("which,n_envs,frames,tile,floor", [
-    ("3", 48, 2000, 32, {"MERGE": 20, "SPLIT": 20, "EJECT": 20, "EAT_VIRUS": 10, "EAT_BLOB": 3, "BLOB_TO_PELLET": 10, "EAT_CELL": 50}),
-    ("r", 24, 1600, 16, {"MERGE": 5, "SPLIT": 5, "EJECT": 5, "EAT_VIRUS": 3, "BLOB_TO_PELLET": 3, "EAT_CELL": 10}),
-    ("4", 6, 640, 32, {"MERGE": 3, "SPLIT": 10, "EJECT": 10, "EAT_VIRUS": 3, "EAT_BLOB": 3, "BLOB_TO_PELLET": 3, "EAT_CELL": 50})])
+    ("3", 48, 2000, 32, {"MERGE": 400, "SPLIT": 200, "EJECT": 200, "EAT_VIRUS": 100, "EAT_BLOB": 100, "VIRUS_EAT_BLOB": 3,
+                         "BLOB_TO_PELLET": 80, "EAT_CELL": 1000, "PLAYER_DIED": 100}),
+    ("r", 24, 1600, 16, {"MERGE": 50, "SPLIT": 100, "EJECT": 80, "EAT_VIRUS": 30, "EAT_BLOB": 30, "VIRUS_EAT_BLOB": 3,
+                         "BLOB_TO_PELLET": 40, "EAT_CELL": 400}),
+    ("4", 6, 1200, 32, {"MERGE": 30, "SPLIT": 70, "EJECT": 50, "EAT_VIRUS": 30, "EAT_BLOB": 20, "BLOB_TO_PELLET": 30,
+                        "EAT_CELL": 500, "PLAYER_DIED": 100})])
 def test_gpu_stress_rare_paths(torch_cuda, which, n_envs, frames, tile, floor):
     """Long multi-env runs, CUDA vs the oracle (itself == the reference bit for bit): observations / rewards / flags every
     frame, whole records + event logs every 40 frames, with a floor on how often each rare path fired (oracle's event log)."""

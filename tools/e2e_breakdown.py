@@ -1,95 +1,99 @@
-"""Where does a synchronous agar_step_host call spend its time?  (4096 envs, 8 frames per call)"""
-import os
-import sys
-import time
-
+"""Where the time of one host-buffer step goes (run on a GPU box): python tools/e2e_breakdown.py [envs]
+ a) device buffers only: agar_step_observe + stream sync                      (kernel + launch + sync)
+ b) agar_step_host, pinned buffers, reward / done only (obs_host = NULL)      (+ flag polling instead of the sync)
+ c) agar_step_host, pinned buffers, observations too                          (+ E x L x 4 bytes over PCIe from the CTAs)
+ d) c) in G env groups on their own streams, launches paced                   (PCIe of one group under the frames of the others)
+"""
+import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-
 import aigar_b200.layout as lay
 from aigar_b200.env import AgarBatch
 
 E = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 cfg = lay.derive_config()
-b = AgarBatch(cfg, E, seed=1)
-L = b.layout
-acts = torch.rand((64, E, 1, 4)).pin_memory()
-acts_np = acts.numpy()
-obs_h = torch.empty((E, 1, L.state_len)).pin_memory()
-rew_h = torch.empty((E, 1)).pin_memory()
-done_h = torch.empty((E, 1), dtype=torch.uint8).pin_memory()
-d_act = torch.rand((E, 1, 4), device=b.device)
 N = 400
 
 
-def timeit(name, f):
-    for i in range(20):
-        f(i)
+def timed(fn, n=N):
+    for _ in range(20):
+        fn()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for i in range(N):
-        f(i)
+    for _ in range(n):
+        fn()
     torch.cuda.synchronize()
-    dt = (time.perf_counter() - t0) / N
-    print("%-46s %8.1f us/call  -> %.3g env-steps/s" % (name, dt * 1e6, E * 8 / dt), flush=True)
+    return (time.perf_counter() - t0) / n * 1e6
 
 
-o, r, d = obs_h.numpy(), rew_h.numpy(), done_h.numpy()
-timeit("step_host (actions H2D, obs+reward+done D2H)", lambda i: b.step_host(acts_np[i % 64], 8, o, r, d))
-timeit("step_observe on device + sync", lambda i: (b.step_observe(d_act, 8), torch.cuda.synchronize()))
-timeit("step_observe on device, no sync", lambda i: b.step_observe(d_act, 8))
-dob = b.observe()
-timeit("obs D2H only + sync", lambda i: (obs_h.copy_(dob.view_as(obs_h), non_blocking=True), torch.cuda.synchronize()))
-timeit("actions H2D only + sync", lambda i: (d_act.copy_(acts[i % 64], non_blocking=True), torch.cuda.synchronize()))
-for W in (4, 16, 32):
-    try:
-        b.set_tile_width(W)
-        timeit("step_host, tile width %d" % W, lambda i: b.step_host(acts_np[i % 64], 8, o, r, d))
-    except Exception as ex:
-        print("W", W, ex)
+b = AgarBatch(cfg, E, seed=1)
+L = b.layout
+acts_d = torch.rand((E, 1, 4), device="cuda")
+b.observe()
+s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+b.step_observe(acts_d, 8)
+torch.cuda.synchronize()
+s.record()
+for _ in range(N):
+    b.step_observe(acts_d, 8)
+e.record()
+torch.cuda.synchronize()
+print("kernel alone (back-to-back launches, CUDA events): %.1f us per 8-frame step of %d envs" % (s.elapsed_time(e) / N * 1e3, E))
 
-# ---- G groups of E/G envs, each handle on its own stream, pipelined through agar_step_host_begin / _end
+
+def dev():
+    b.step_observe(acts_d, 8)
+    torch.cuda.synchronize()
+
+
+print("a) device buffers + sync:          %.1f us" % timed(dev))
+acts = torch.rand((E, 1, 4)).pin_memory()
+obs_h = torch.empty((E, 1, L.state_len)).pin_memory()
+rew_h = torch.empty((E, 1)).pin_memory()
+done_h = torch.empty((E, 1), dtype=torch.uint8).pin_memory()
+ap, op, rp, dp = acts.data_ptr(), obs_h.data_ptr(), rew_h.data_ptr(), done_h.data_ptr()
+
+
+def host_noobs():
+    b.step_host_begin_ptr(ap, 8, None)
+    b.step_host_end_ptr(rp, dp)
+
+
+def host_obs():
+    b.step_host_begin_ptr(ap, 8, op)
+    b.step_host_end_ptr(rp, dp)
+
+
+print("b) pinned, reward/done only, poll: %.1f us" % timed(host_noobs))
+print("c) pinned, + observations (%.2f MB): %.1f us" % (obs_h.numel() * 4 / 1e6, timed(host_obs)))
+b.close()
 for G in (2, 4):
-    n = E // G
-    groups = [AgarBatch(cfg, n, seed=1, first_env_id=g * n) for g in range(G)]
-    streams = [torch.cuda.Stream() for _ in range(G)]
-    bufs = [(torch.empty((n, 1, L.state_len)).pin_memory().numpy(), torch.empty((n, 1)).pin_memory().numpy(),
-             torch.empty((n, 1), dtype=torch.uint8).pin_memory().numpy()) for _ in range(G)]
+    Eg = E // G
+    hs = [AgarBatch(cfg, Eg, seed=1, first_env_id=g * Eg, stream=torch.cuda.Stream()) for g in range(G)]
+    for h in hs:
+        h.observe()
+    ptrs = [(acts[g * Eg:].data_ptr(), obs_h[g * Eg:].data_ptr(), rew_h[g * Eg:].data_ptr(), done_h[g * Eg:].data_ptr()) for g in range(G)]
+    for spacing_us in (0, 10, 20, 30, 40):
+        sp = spacing_us * 1e-6
+        last = [0.0]
 
-    def begin(g, i):
-        with torch.cuda.stream(streams[g]):
-            groups[g].step_host_begin(acts_np[i % 64, g * n:(g + 1) * n], 8, bufs[g][0])
+        def go(g):
+            while time.perf_counter() - last[0] < sp:
+                pass
+            hs[g].step_host_begin_ptr(ptrs[g][0], 8, ptrs[g][1])
+            last[0] = time.perf_counter()
 
-    def end(g):
-        with torch.cuda.stream(streams[g]):
-            groups[g].step_host_end(bufs[g][1], bufs[g][2])
-
-    for g in range(G):
-        begin(g, 0)
-
-    def cycle(i):
         for g in range(G):
-            end(g)          # group g's observations are on the host: a policy would produce its next actions here
-            begin(g, i + 1)
-
-    timeit("%d groups of %d envs pipelined (begin/end)" % (G, n), cycle)
-    for g in range(G):
-        end(g)
-
-# ---- CPU cost of the enqueue half against the wait half (one group)
-tb = te = 0.0
-for i in range(N):
-    t0 = time.perf_counter()
-    b.step_host_begin(acts_np[i % 64], 8, o)
-    t1 = time.perf_counter()
-    b.step_host_end(r, d)
-    t2 = time.perf_counter()
-    tb += t1 - t0
-    te += t2 - t1
-print("one group: begin (enqueue, CPU) %.1f us, end (wait + unpack) %.1f us" % (tb / N * 1e6, te / N * 1e6))
-lib, h, st = b.lib, b.h, b._stream()
-pa, po, pr, pd = acts_np[0].ctypes.data, o.ctypes.data, r.ctypes.data, d.ctypes.data
-t0 = time.perf_counter()
-for i in range(N):
-    lib.agar_step_host(h, pa, 8, po, pr, pd, st)
-print("raw ctypes agar_step_host, pointers precomputed: %.1f us/call" % ((time.perf_counter() - t0) / N * 1e6))
+            go(g)
+        torch.cuda.synchronize
+        t0 = time.perf_counter()
+        for _ in range(N):
+            for g in range(G):
+                hs[g].step_host_end_ptr(ptrs[g][2], ptrs[g][3])
+                go(g)
+        for g in range(G):
+            hs[g].step_host_end_ptr(ptrs[g][2], ptrs[g][3])
+        dt = (time.perf_counter() - t0) / N * 1e6
+        print("d) %d groups, spacing %2d us: %.1f us per step of all %d envs" % (G, spacing_us, dt, E))
+    for h in hs:
+        h.close()
