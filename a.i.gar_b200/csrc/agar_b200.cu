@@ -73,14 +73,37 @@ __device__ __forceinline__ void bind_ctx(Ctx<W>& c, const DevParams& P, int tile
     if (P.stage >= 2) {
         uint8_t* hot = g_smem + (size_t)tiles * P.scratch_bytes + (size_t)tile_id * pel_cache_bytes(P);
         c.pel = (uint32_t*)(hot + hot_a_bytes(P));
-        if (P.hot_a > 0) { /* header .. viruses are contiguous from byte 0 of the record */
+        /* header, players, cells, viruses are contiguous from byte 0 of the record: whichever of them end inside the cached
+         * prefix [0, hot_a) are served from shared memory (stage 4 caches header + players only: the bot bookkeeping and the
+         * command / fov fields every lane-0 bot turn walks through) */
+        if (P.hot_a >= (int)P.L.off_cells) {
             c.h = (AgarEnvHeader*)(hot + P.L.off_header);
             c.pl = (AgarPlayer*)(hot + P.L.off_players);
-            c.cells = (AgarCell*)(hot + P.L.off_cells);
-            c.vir = (AgarMote*)(hot + P.L.off_viruses);
         }
+        if (P.hot_a >= (int)P.L.off_viruses) c.cells = (AgarCell*)(hot + P.L.off_cells);
+        if (P.hot_a >= (int)P.L.off_blobs) c.vir = (AgarMote*)(hot + P.L.off_viruses);
     }
 }
+
+#ifdef AGAR_PHASE_CLOCKS
+/* debug build only (tools/phase_clocks.py): cycles each env's tile spent per frame phase, summed over the launch */
+
+#define CLK_MARK(slot)                                                      \
+    do {                                                                    \
+        if (active) clk_mark(c, slot);                                      \
+    } while (0)
+extern "C" int agar_debug_read_clocks(unsigned long long* host, int n_envs, int reset) {
+    if (cudaMemcpyFromSymbol(host, g_clk, (size_t)n_envs * 16 * 8) != cudaSuccess) return -1;
+    if (reset) {
+        void* p = nullptr;
+        cudaGetSymbolAddress(&p, g_clk);
+        cudaMemset(p, 0, sizeof(unsigned long long) * 32768 * 16);
+    }
+    return 0;
+}
+#else
+#define CLK_MARK(slot) do { } while (0)
+#endif
 
 /* ------------------------------------------------------------------ the step kernel */
 template <int W, bool FULL, int MAXT>
@@ -118,14 +141,20 @@ k_main(const __grid_constant__ DevParams P, uint8_t* __restrict__ state, const f
         for (int it = 0; it <= total; ++it) {
             const bool last = it == total;
             if (last && !(flags & KF_OBS_AFTER)) break;
+#ifdef AGAR_PHASE_CLOCKS
+            c.clk_t = clock64(), c.clk_env = env;
+#endif
             if (psync) __syncthreads();
+            CLK_MARK(0); /* (ptxas hoists this clock read above the barrier: the wait lands in the NEXT slot, the fov pass) */
             const int f = n_frames > 0 ? it % n_frames : 0, d = n_frames > 0 ? it / n_frames : 0;
             const bool emit = last || (f == 0 && (flags & KF_OBS_BEFORE)); /* observations leave the kernel here */
             if (active && !last && c.lane == 0) c.h->n_events = 0;
             if (FULL && K > 1 && active && !last) { /* every alive player's turn below would compute its own, on lane 0 */
                 update_all_fovs(c, P);
                 c.fov_done = true;
+                CLK_MARK(8); /* fov pass */
                 if (K * P.L.cell_cap > W) build_live_cells(c, P); /* one iteration covers all slots otherwise */
+                CLK_MARK(11); /* live-cell list */
             }
             for (int k = 0; k < K; ++k) {
                 if (psync_bots && k > 0) __syncthreads(); /* one bot turn per barrier interval */
@@ -150,20 +179,26 @@ k_main(const __grid_constant__ DevParams P, uint8_t* __restrict__ state, const f
                         }
                         c.t.sync();
                     } else if (FULL && !last) {
+                        CLK_MARK(1); /* NN turns so far */
                         scripted_turn(c, P, k);
+                        CLK_MARK(7); /* scripted (greedy / random) turns */
                     }
                 }
             }
             if (last) break;
+            CLK_MARK(1); /* bot turns */
             c.fov_done = false, c.n_live = -1;
             for (int ph = 0; ph < AGAR_FIELD_PHASES; ++ph) {
                 if (ph == 0 ? psync : psync_field) __syncthreads();
+                if (ph == 0) CLK_MARK(2); /* wait at the field barrier */
                 if (active) field_update_phase<W, FULL>(c, P, ph);
+                CLK_MARK(3 + ph); /* 3: viruses / blobs / players  4: merge, virus overlaps  5: pellets  6: blobs, player-player, spawn */
             }
             if (active) {
                 if (c.lane == 0) c.h->frame += 1;
                 c.t.sync();
             }
+            CLK_MARK(12); /* frame tail */
         }
         if (active && c.lane == 0 && (P.turn_reward || P.turn_done))
             for (int a = 0; a < A; ++a) {
@@ -616,6 +651,12 @@ extern "C" int agar_create(const AgarConfig* cfg, int n_envs, int device, uint64
     P.full = e->full;
     int vel_bytes = e->full ? L.n_players * L.cell_cap * 2 * 8 : 0;
     int obs_bytes = obs_scratch_bytes(L.grid_squares, e->full != 0);
+    /* the pellet index (agar_dev.cuh) lives in the same scratch: it is built after the players have moved (velocities dead)
+     * and before the next bot phase (observation tables dead); pools of <= 8 chunks are scanned directly */
+    P.pel_index = e->full && L.pellet_cap > 256 && !(getenv("AGAR_PEL_INDEX") && atoi(getenv("AGAR_PEL_INDEX")) == 0);
+    const int gb_idx = (P.S + 9) / 10; /* AG_IDX_CELL */
+    int idx_bytes = P.pel_index ? ((gb_idx * gb_idx + 3) & ~1) * 2 + L.pellet_cap * 2 + 128 + 16 : 0;
+    if (idx_bytes > vel_bytes) vel_bytes = idx_bytes;
     P.scratch_bytes = ((vel_bytes > obs_bytes ? vel_bytes : obs_bytes) + 15) / 16 * 16 + 8;
     P.live_off = P.scratch_bytes; /* live-cell list: uint16 per cell slot, after the observation / velocity scratch */
     if (e->full) P.scratch_bytes += (L.n_players * L.cell_cap * 2 + 15) / 16 * 16;
@@ -632,7 +673,7 @@ extern "C" int agar_create(const AgarConfig* cfg, int n_envs, int device, uint64
         P.stage = hot3 * 12 <= 200 * 1024 ? 3 : 2;
     }
     if (getenv("AGAR_STAGE")) P.stage = atoi(getenv("AGAR_STAGE"));
-    P.hot_a = P.stage == 3 ? (int)L.off_blobs : 0;
+    P.hot_a = P.stage == 3 ? (int)L.off_blobs : (P.stage == 4 ? (int)L.off_cells : 0);
     /* multi-agent kernels are instruction-fetch bound: lock-step the CTA's warps phase by phase (measured 2x) */
     P.phase_sync = getenv("AGAR_PHASE_SYNC") ? atoi(getenv("AGAR_PHASE_SYNC")) : e->full;
     double speed_modifier = 1.0 / 30;

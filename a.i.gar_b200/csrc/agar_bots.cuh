@@ -480,7 +480,9 @@ DEV void nn_turn_begin(Ctx<W>& c, const DevParams& P, int k, float* obs) {
         B->turn_begun = 1;
     }
     do_obs = c.t.shfl(do_obs, 0);
+    CLK_IN(c, 9); /* reward / frame-skip bookkeeping */
     if (do_obs) observe_agent<W, FULL>(c, P, k, k, obs);
+    CLK_IN(c, 10); /* observation */
 }
 /* lane 0; second half of move_NN (bot.py:223-232) + tail of makeMove (:256-270) */
 template <int W>

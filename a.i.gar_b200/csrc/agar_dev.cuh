@@ -15,6 +15,7 @@
  */
 #pragma once
 #include <cooperative_groups.h>
+#include <cooperative_groups/reduce.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -44,6 +45,7 @@ struct DevParams {
     double pow_n[17];
     const double* deg_tab; /* cos(d*pi/180)[360], sin(...)[360] — host libm, exactly the oracle's table */
     uint64_t seed, first_env;
+    int pel_index; /* 1: multi-agent configs with a large pellet pool build the per-env bucket index every frame (agar_dev.cuh) */
     int hot_a, live_off; /* live_off: offset of the live-cell list in a tile's scratch (multi-agent configs) */ /* stage >= 2: bytes [0, hot_a) of a record (header, players, cells, viruses) are cached in shared memory too */
     /* optional per-launch outputs of the last bot turn ([E][A]); NULL = use agar_get */
     float* turn_reward;
@@ -76,10 +78,29 @@ struct Ctx {
     float* hist;
     AgarEvent* ev;
     uint8_t* scratch;
+#ifdef AGAR_PHASE_CLOCKS
+    long long clk_t;
+    int clk_env;
+#endif
     bool fov_done; /* this frame's fields of view were computed up front for every player (update_all_fovs) */
     int n_live;    /* >= 0: live_cells() lists the (player * cell_cap + cell) indices of all live cells, canonical order */
     __device__ Ctx(cg::thread_block_tile<W> tile) : t(tile), fov_done(false), n_live(-1) {}
 };
+
+#ifdef AGAR_PHASE_CLOCKS
+__device__ unsigned long long g_clk[32768 * 16];
+template <int W>
+__device__ __forceinline__ void clk_mark(Ctx<W>& c, int slot) {
+    if (c.lane == 0 && c.clk_env < 32768) {
+        const long long now = clock64();
+        g_clk[(size_t)c.clk_env * 16 + slot] += (unsigned long long)(now - c.clk_t);
+        c.clk_t = now;
+    }
+}
+#define CLK_IN(c, slot) clk_mark(c, slot)
+#else
+#define CLK_IN(c, slot) do { } while (0)
+#endif
 
 #define CELLP(c, P, k, i) (&(c).cells[(k) * (P).L.cell_cap + (i)])
 
@@ -647,7 +668,35 @@ DEVN void player_rare_path(Ctx<W>& c, const DevParams& P, int k, double* vel) {
             log_ev(c, P, AGAR_EV_EJECT, k, (int)q->uid, c.h->n_blobs, 0);
             c.h->n_blobs += 1;
         }
-    /* handlePlayerCollisions field.py:149-181 */
+}
+
+/* cooperative: handlePlayerCollisions (field.py:149-181) — the same-player push-apart, a Gauss-Seidel sweep over the ORDERED
+ * pairs (i, j), j != i, with immediate position updates.  At steady state a split player holds up to 16 cells that sit exactly
+ * touching one another, so the reference's 240 sequential pair tests (a sqrt each) with ~10 adjustments per player and frame
+ * were the largest single-lane loop of the multi-agent kernel (27 % of all instructions of the 1-vs-greedy config, and the
+ * main source of CTA-barrier imbalance).  Exact parallel form: every lane tests its share of the 16 x 16 pair slots on the
+ * current positions; the tile takes the FIRST hit in pair order, lane 0 applies the adjustment with the reference's arithmetic,
+ * and only the pairs after it that involve one of the two moved cells are re-tested (a test depends on nothing else).  Pairs
+ * before the current one are never revisited, exactly as in the sequential sweep.  The sqrt is only evaluated inside the
+ * rounding band of `dist < sum` (d2 against sum^2 with a 1e-12 margin decides everything else identically). */
+DEV bool self_collision_test(const AgarCell* base, int n, int i, int j) {
+    if (i >= n || j >= n || i == j) return false;
+    const AgarCell* a = &base[i];
+    const AgarCell* b = &base[j];
+    if (a->counter > 0 || b->counter > 0 || (a->merge_time <= 0 && b->merge_time <= 0)) return false;
+    const double d2 = (a->x - b->x) * (a->x - b->x) + (a->y - b->y) * (a->y - b->y);
+    const double sum = a->radius + b->radius, s2 = sum * sum;
+    if (d2 > s2 * (1.0 + 1e-12) || d2 == 0.0) return false;
+    if (d2 < s2 * (1.0 - 1e-12)) return true;
+    const double dist = sqrt(d2);
+    return dist < sum && dist != 0;
+}
+/* lane 0: the sequential sweep (tiles narrower than a warp, where the cooperative form below does not fit) */
+template <int W>
+DEV void self_collisions_seq(Ctx<W>& c, const DevParams& P, int k) {
+    AgarPlayer* p = &c.pl[k];
+    AgarCell* base = CELLP(c, P, k, 0);
+    const double S = (double)P.S;
     for (int i = 0; i < p->n_cells; ++i) {
         AgarCell* a = &base[i];
         if (a->counter > 0) continue;
@@ -670,6 +719,72 @@ DEVN void player_rare_path(Ctx<W>& c, const DevParams& P, int k, double* vel) {
                 big->x = clampS(nbx, S), big->y = clampS(nby, S);
                 sm->x = clampS(nsx, S), sm->y = clampS(nsy, S);
             }
+        }
+    }
+}
+/* W == 32.  Lane r < 16 keeps row r of the 16 x 16 hit matrix (bit j: the ordered pair (r, j) collides on the current
+ * positions).  After an adjustment of (i, j) only rows i, j and columns i, j can change: lanes 0..15 re-test row i, lanes
+ * 16..31 row j (one test each, gathered with a ballot), then the same for the two columns (each lane folds its own bit in). */
+template <int W>
+DEV void player_self_collisions(Ctx<W>& c, const DevParams& P, int k) {
+    AgarPlayer* p = &c.pl[k];
+    const int n = p->n_cells;
+    if (n < 2) return;
+    if (W != 32) {
+        if (c.lane == 0) self_collisions_seq(c, P, k);
+        return;
+    }
+    AgarCell* base = CELLP(c, P, k, 0);
+    const double S = (double)P.S;
+    const int r = c.lane & 15, half = c.lane >> 4;
+    unsigned row = 0;
+    { /* initial matrix: lane (r, half) tests columns [8 half, 8 half + 8) of row r */
+        unsigned part = 0;
+        const int j0 = half * 8, j1 = min(n, j0 + 8);
+        if (r < n)
+            for (int j = j0; j < j1; ++j)
+                if (self_collision_test(base, n, r, j)) part |= 1u << j;
+        row = part | c.t.shfl_xor(part, 16);
+    }
+    int ci = -1, cj = -1; /* the pair processed last: everything up to it in (i, j) order is done */
+    while (true) {
+        unsigned m = row;
+        if (r < ci) m = 0;
+        else if (r == ci) m &= ~((2u << cj) - 1u);
+        const int mine = (half == 0 && m) ? r * 16 + __ffs((int)m) - 1 : 0x7fffffff;
+        const int first = cg::reduce(c.t, mine, cg::less<int>());
+        if (first == 0x7fffffff) break;
+        const int i = first >> 4, j = first & 15;
+        if (c.lane == 0) {
+            AgarCell *a = &base[i], *b = &base[j];
+            double d2 = (a->x - b->x) * (a->x - b->x) + (a->y - b->y) * (a->y - b->y);
+            double dist = sqrt(d2), sum = a->radius + b->radius;
+            log_ev(c, P, AGAR_EV_COLLIDE, k, (int)a->uid, (int)b->uid, 0);
+            AgarCell *big, *sm;
+            if (a->mass > b->mass)
+                big = a, sm = b;
+            else
+                big = b, sm = a;
+            double ds = (sum - dist) / dist, q = sm->mass / big->mass;
+            double xs = (big->x - sm->x) * ds, ys = (big->y - sm->y) * ds;
+            double nbx = big->x + xs * q, nby = big->y + ys * q;
+            double nsx = sm->x - xs * (1 - q), nsy = sm->y - ys * (1 - q);
+            big->x = clampS(nbx, S), big->y = clampS(nby, S);
+            sm->x = clampS(nsx, S), sm->y = clampS(nsy, S);
+        }
+        c.t.sync();
+        ci = i, cj = j;
+        { /* rows i (lanes 0..15) and j (lanes 16..31) */
+            const bool h = self_collision_test(base, n, half ? j : i, r);
+            const unsigned bal = c.t.ballot(h);
+            if (r == i) row = bal & 0xffffu;
+            if (r == j) row = bal >> 16;
+        }
+        { /* columns i (lanes 0..15 test (r, i)) and j (lanes 16..31 test (r, j)): lane r folds both bits into its row */
+            const bool h = self_collision_test(base, n, r, half ? j : i);
+            const unsigned bal = c.t.ballot(h);
+            const unsigned bi = (bal >> r) & 1u, bj = (bal >> (16 + r)) & 1u;
+            row = (row & ~((1u << i) | (1u << j))) | (bi << i) | (bj << j);
         }
     }
 }
@@ -737,6 +852,8 @@ DEV void update_players(Ctx<W>& c, const DevParams& P) {
         bool rare = p->do_split || p->do_eject || p->n_cells > 1;
         if (rare) {
             if (c.lane == 0) player_rare_path(c, P, k, vel);
+            c.t.sync(); /* positions (and a split's new cells) are visible to the tile */
+            player_self_collisions<W>(c, P, k);
         } else if (c.lane == 0) {
             AgarCell* q = CELLP(c, P, k, 0);
             update_pos(q->x, q->y, vel[(size_t)k * cap * 2], vel[(size_t)k * cap * 2 + cap], q->svx, q->svy, q->counter, S);
@@ -898,15 +1015,161 @@ DEVN void player_virus_overlap_seq(Ctx<W>& c, const DevParams& P) {
     }
 }
 
+/* ---- per-env pellet index (north star (3): a per-env uniform grid built by a shared-memory counting sort).  The INTEGER
+ * pellet pool is bucketed by the pellet's own point on a 10-unit grid — finer than the reference's 20-unit hash table
+ * (spatialHashTable.py:49-83): the reference's table only decides which pairs get TESTED, and a pair that fails the overlap
+ * test has no effect whatsoever, so any index that returns a superset of the pellets a cell can actually eat is equivalent
+ * (the exact bucket-rectangle condition of the reference's candidate list is still applied per pellet, and eaten pellets are
+ * taken in canonical slot order).  Rebuilt once per frame in the tile's scratch: count (shared-memory atomics on packed uint16
+ * pairs) -> exclusive scan over the gb x gb buckets -> scatter.  Layout: uint16 cnt[gb2 + 2] (after the scatter cnt[b] = END of
+ * bucket b, so bucket b = [b ? cnt[b - 1] : 0, cnt[b])), uint16 ent[pellet_cap] (pool slots), uint16 tmp[64]. */
+#define AG_IDX_CELL 10
+DEV int pel_index_gb(const DevParams& P) { return (P.S + AG_IDX_CELL - 1) / AG_IDX_CELL; }
+DEV int pel_index_cnt_len(const DevParams& P) { return (pel_index_gb(P) * pel_index_gb(P) + 2 + 1) & ~1; }
+DEV bool pel_index_enabled(const DevParams& P) { return P.full && P.pel_index; }
+template <int W>
+DEV void build_pellet_index(Ctx<W>& c, const DevParams& P) {
+    const int gb = pel_index_gb(P), gb2 = gb * gb, cap = P.L.pellet_cap, nc = pel_index_cnt_len(P);
+    uint16_t* cnt = (uint16_t*)c.scratch;
+    uint32_t* cnt32 = (uint32_t*)c.scratch; /* two counters per word: counts stay below 65536, the halves never carry */
+    uint16_t* ent = cnt + nc;
+    for (int i = c.lane; i < nc / 2; i += W) cnt32[i] = 0;
+    c.t.sync();
+    for (int s = c.lane; s < cap; s += W) {
+        const uint32_t pk = c.pel[s];
+        if (!pk) continue;
+        const int b = (AGAR_PELLET_Y(pk) / AG_IDX_CELL) * gb + AGAR_PELLET_X(pk) / AG_IDX_CELL;
+        atomicAdd(&cnt32[b >> 1], (b & 1) ? 0x10000u : 1u);
+    }
+    c.t.sync();
+    /* exclusive scan: lane l owns the consecutive buckets [l * per, l * per + per) */
+    const int per = (gb2 + W - 1) / W;
+    uint32_t local = 0;
+    for (int i = 0; i < per; ++i) {
+        const int b = c.lane * per + i;
+        if (b < gb2) local += cnt[b];
+    }
+    uint32_t incl = local;
+    for (int off = 1; off < W; off <<= 1) {
+        const uint32_t v = c.t.shfl_up(incl, off);
+        if (c.lane >= off) incl += v;
+    }
+    uint32_t run = incl - local;
+    for (int i = 0; i < per; ++i) {
+        const int b = c.lane * per + i;
+        if (b < gb2) {
+            const uint32_t n = cnt[b];
+            cnt[b] = (uint16_t)run;
+            run += n;
+        }
+    }
+    c.t.sync();
+    for (int s = c.lane; s < cap; s += W) {
+        const uint32_t pk = c.pel[s];
+        if (!pk) continue;
+        const int b = (AGAR_PELLET_Y(pk) / AG_IDX_CELL) * gb + AGAR_PELLET_X(pk) / AG_IDX_CELL;
+        const uint32_t old = atomicAdd(&cnt32[b >> 1], (b & 1) ? 0x10000u : 1u);
+        ent[(b & 1) ? (old >> 16) : (old & 0xffffu)] = (uint16_t)s;
+    }
+    c.t.sync();
+}
+
+/* cooperative, W == 32: one cell's pellet eating through the index.  Returns false (nothing done) if the candidate set is too
+ * large for the scratch list — the caller then runs the full scan, which is always correct.
+ *   1. window: every pellet the chain can eat lies within R >= r_final + 1 of the centre, r_final <= radius(mass + 3 x pellets in
+ *      the window); R starts at radius + 2 and is widened until that bound holds (almost always at once);
+ *   2. the window's entries (a contiguous range per bucket row) are filtered with the reference's candidate condition and a
+ *      CONSERVATIVE overlap test against the largest radius the cell can reach; survivors (usually 0-3) go to a short list;
+ *   3. the list is consumed in ascending slot order (tile-min), each pellet tested against the cell as grown so far: the
+ *      reference's sequential eat chain, exactly. */
+template <int W>
+DEV bool cell_eats_pellets_indexed(Ctx<W>& c, const DevParams& P, int k, int ci, const Rect& rc, double& cm, double& cr, uint32_t uid) {
+    const int gb = pel_index_gb(P), nc = pel_index_cnt_len(P);
+    const uint16_t* cnt = (const uint16_t*)c.scratch;
+    const uint16_t* ent = cnt + nc;
+    uint16_t* tmp = (uint16_t*)(ent + P.L.pellet_cap);
+    const double cx = CELLP(c, P, k, ci)->x, cy = CELLP(c, P, k, ci)->y;
+    int R = (int)cr + 2, bx0, bx1, by0, by1, total;
+    double m_max, r_max;
+    for (int pass = 0;; ++pass) {
+        if (pass == 4) return false;
+        bx0 = max(0, ((int)floor(cx) - R) / AG_IDX_CELL), bx1 = min(gb - 1, ((int)floor(cx) + R + 1) / AG_IDX_CELL);
+        by0 = max(0, ((int)floor(cy) - R) / AG_IDX_CELL), by1 = min(gb - 1, ((int)floor(cy) + R + 1) / AG_IDX_CELL);
+        if ((int)floor(cx) - R < 0) bx0 = 0;
+        if ((int)floor(cy) - R < 0) by0 = 0;
+        total = 0;
+        for (int by = by0 + c.lane; by <= by1; by += W) {
+            const int b0 = by * gb + bx0, b1 = by * gb + bx1;
+            total += (int)cnt[b1] - (b0 ? (int)cnt[b0 - 1] : 0);
+        }
+        total = cg::reduce(c.t, total, cg::plus<int>());
+        m_max = cm + 3.0 * total;
+        if (!(m_max < AG_MAX_MASS)) m_max = AG_MAX_MASS;
+        r_max = radius_of(m_max);
+        if ((int)r_max + 2 <= R) break;
+        R = (int)r_max + 2;
+    }
+    if (total == 0) return true;
+    /* 2. filter into the short list */
+    const double rr = r_max > 1.0 ? r_max * r_max : 1.0;
+    int n_list = 0;
+    for (int by = by0; by <= by1; ++by) {
+        const int b0 = by * gb + bx0, b1 = by * gb + bx1;
+        const int beg = b0 ? (int)cnt[b0 - 1] : 0, end = (int)cnt[b1];
+        for (int base = beg; base < end; base += W) {
+            const int e = base + c.lane;
+            const int slot = e < end ? (int)ent[e] : -1;
+            const uint32_t pk = slot >= 0 ? c.pel[slot] : 0u;
+            const int px = AGAR_PELLET_X(pk), py = AGAR_PELLET_Y(pk), pm = AGAR_PELLET_M(pk);
+            const double dx = cx - (double)px, dy = cy - (double)py;
+            const bool poss = pk != 0 && rect_hit(rc, pellet_rect(px, py)) && (dx * dx + dy * dy) * 1.1 < rr * (1.0 + 1e-9) &&
+                              m_max > 1.25 * (double)pm;
+            const unsigned bal = c.t.ballot(poss);
+            if (bal) {
+                const int pos = n_list + __popc(bal & ((1u << c.lane) - 1u));
+                if (poss && pos < 64) tmp[pos] = (uint16_t)slot;
+                n_list += __popc(bal);
+            }
+        }
+    }
+    if (n_list == 0) return true;
+    if (n_list > 64) return false;
+    c.t.sync();
+    /* 3. ordered chain over the short list: lane l holds entries l and l + 32 */
+    int s0 = c.lane < n_list ? (int)tmp[c.lane] : 0x7fffffff, s1 = c.lane + 32 < n_list ? (int)tmp[c.lane + 32] : 0x7fffffff;
+    while (true) {
+        const int first = cg::reduce(c.t, min(s0, s1), cg::less<int>());
+        if (first == 0x7fffffff) break;
+        if (s0 == first) s0 = 0x7fffffff;
+        if (s1 == first) s1 = 0x7fffffff;
+        const uint32_t pk = c.pel[first];
+        const int px = AGAR_PELLET_X(pk), py = AGAR_PELLET_Y(pk), pm = AGAR_PELLET_M(pk);
+        if (overlap(cx, cy, cm, cr, (double)px, (double)py, (double)pm, P.pellet_r[pm & 3]) && cm > 1.25 * (double)pm) {
+            double nm = cm + (double)pm;
+            if (!(nm < AG_MAX_MASS)) nm = AG_MAX_MASS;
+            cm = nm;
+            cr = radius_of(nm);
+            c.t.sync(); /* every lane has read the slot */
+            if (c.lane == 0) {
+                log_ev(c, P, AGAR_EV_EAT_PELLET, k, (int)uid, first, 0);
+                c.pel[first] = 0;
+                c.h->n_pellets -= 1;
+            }
+        }
+    }
+    return true;
+}
+
 /* cooperative: the hot loop.  field.py:207-213 + eatPellet :327-344.  For one cell (k, ci): integer pellets in slot
  * order, then float ("fat") pellets in slot order; the eat chain is sequential — a pellet is tested against the
  * cell as grown by every earlier eat — but hits are found 32 pellets at a time with a ballot. */
 template <int W>
-DEV void cell_eats_pellets(Ctx<W>& c, const DevParams& P, int k, int ci, bool fat_too) {
+DEV void cell_eats_pellets(Ctx<W>& c, const DevParams& P, int k, int ci, bool fat_too, bool indexed = false) {
     AgarCell* q = CELLP(c, P, k, ci);
     double cx = q->x, cy = q->y, cm = q->mass, cr = q->radius;
     const Rect rc = rect_of(P.S, cx, cy, cr); /* candidates are fixed before the cell grows */
-    const int cap = P.L.pellet_cap;
+    const bool by_index = W == 32 && indexed && cell_eats_pellets_indexed(c, P, k, ci, rc, cm, cr, q->uid);
+    const int cap = by_index ? 0 : P.L.pellet_cap; /* the index served this cell: no scan of the pool */
     /* Integer window: a pellet can only be eaten if it lies within the cell's radius, and within one chunk of W
      * pellets the cell gains at most 3 W mass — so nothing outside |d| <= radius(mass + 3 W) + 2 matters for the
      * chunk at hand.  The window only skips chunks; hits are decided by the exact tests below.  It is
@@ -1147,9 +1410,11 @@ DEV void field_update_phase(Ctx<W>& c, const DevParams& P, int phase) {
             cell_eats_pellets(c, P, 0, 0, false);
         } else {
             bool fat_too = P.L.fat_cap > 0;
+            const bool indexed = W == 32 && pel_index_enabled(P);
+            if (indexed) build_pellet_index(c, P);
             for (int k = 0; k < P.L.n_players; ++k) {
                 if (!c.pl[k].alive) continue;
-                for (int ci = 0; ci < c.pl[k].n_cells; ++ci) cell_eats_pellets(c, P, k, ci, fat_too && c.h->n_fat > 0);
+                for (int ci = 0; ci < c.pl[k].n_cells; ++ci) cell_eats_pellets(c, P, k, ci, fat_too && c.h->n_fat > 0, indexed);
             }
         }
     } else {

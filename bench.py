@@ -42,16 +42,17 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def profiled_traffic(envs, frames):
-    """dram bytes per launch of k_main from the committed ncu summary, if it matches this launch shape."""
+def profiled_kernel_facts(envs, frames):
+    """What ncu measured for the bench kernel at this launch shape (profiles/traffic.json, written from the committed ncu
+    summary of the same command): DRAM bytes per launch, issue-slot utilisation, warp instructions per env-step."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             t = json.load(f)
         if int(t.get("envs", -1)) == envs and int(t.get("frames", -1)) == frames:
-            return float(t["dram_bytes_per_launch"])
+            return t
     except Exception:
         pass
-    return None
+    return {}
 
 
 class ClockSampler(object):
@@ -71,7 +72,7 @@ class ClockSampler(object):
             os.close(fd)
             self.out = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.out,
+                                          "--format=csv,noheader,nounits", "-lms", "5"], stdout=self.out,
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -108,28 +109,72 @@ class ClockSampler(object):
         return res
 
 
-def cpu_port_throughput(n_threads, target_s=12.0, frames=1000):
-    """The C oracle (oracle/agar_oracle.c, libm build) on the host cores: the CPU baseline / reference arm.
-    Returns (env-steps/s, description of the sample)."""
+CONFIGS = {
+    # BASELINE.json configs[1..3]; bytes = SURVEY §8d's worked algorithmic bytes per env-step (obs every 8th frame)
+    "configs[1]": dict(kw=dict(), envs=4096, bytes=None,
+                       name="pellet collection, 1 RL agent, no opponents/viruses, grid-vision obs"),
+    "configs[2]": dict(kw=dict(num_nn=1, num_greedy=1, virus=True, split=True, eject=True), envs=16384, bytes=2950.0,
+                       name="1 agent vs 1 greedy bot, viruses, splitting and ejection"),
+    "configs[3]": dict(kw=dict(num_nn=8, num_greedy=8, virus=True, split=True, eject=True), envs=8192, bytes=22900.0,
+                       name="multi-agent arena: 8 agents + 8 greedy bots, 1350 pellets, split / merge heavy"),
+}
+
+
+def cpu_port_throughput(n_threads, kw=None, target_s=10.0, frames=1000, max_envs=4096):
+    """The C oracle (oracle/agar_oracle.c, libm build: bit-exact against the Python reference) on the host cores: the CPU
+    baseline / reference arm.  Returns (env-steps/s, description of the bounded sample)."""
     import aigar_b200.layout as lay
     from oracle import oracle as orc
-    cfg = lay.derive_config()
+    cfg = lay.derive_config(**(kw or {}))
     decisions = frames // PERIOD
     t0 = time.perf_counter()
     steps, _ = orc.rollout_batch(cfg, n_threads, 11, 0, 10, n_threads)  # probe: 80 frames per thread
     probe = max(time.perf_counter() - t0, 1e-4)
     rate = steps / probe
-    envs = int(max(n_threads, min(4096, rate * target_s / (decisions * PERIOD))))
+    envs = int(max(n_threads, min(max_envs, rate * target_s / (decisions * PERIOD))))
     envs = max(n_threads, envs // n_threads * n_threads)
     t0 = time.perf_counter()
     steps, _ = orc.rollout_batch(cfg, envs, 11, 0, decisions, n_threads)
     dt = time.perf_counter() - t0
-    return steps / dt, "%d envs x %d frames of the same workload on %d threads (%.1f s)" % (envs, decisions * PERIOD, n_threads, dt)
+    return steps / dt, "sample of %d envs x %d frames of the same workload on %d threads (%.1f s)" % (
+        envs, decisions * PERIOD, n_threads, dt)
+
+
+def python_reference_numbers():
+    """The unpatched Python reference timed in the build container (tools/time_reference.py -> profiles/): it cannot travel to
+    the GPU box, so its numbers are cited, with the machine they were taken on, next to the C port timed here."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_python_reference.json")) as f:
+            d = json.load(f)
+        out = {"source": "profiles/r02_python_reference.json (tools/time_reference.py, build container)",
+               "cpu_model": d["cpu_model"], "cores": d["cores"], "unit": "frames/s"}
+        for k, v in d["configs"].items():
+            out[k] = {"model_update_1core": round(v["model_update_frames_per_s_1core"], 1),
+                      "model_update_pool": round(v["model_update_frames_per_s_pool"], 1),
+                      "field_update_only_1core": round(v["field_update_only_frames_per_s_1core"], 1),
+                      "get_state_representation_1core": round(v["get_state_representation_obs_per_s_1core"], 1)}
+        return out
+    except Exception:
+        return None
+
+
+def workload_name(envs, frames, key="configs[1]"):
+    return ("%s: %s; %d envs per GPU, random-action driver, %d-frame rollouts (frame-skip 7, obs every 8th frame; "
+            "observations in the reference's own binning, AGAR_OBS_REFERENCE)" % (key, CONFIGS[key]["name"], envs, frames))
+
+
+def base_config(E, frames, world):
+    """`config` of the JSON line — the SAME dict in the GPU arm and in the reference (CPU) arm, so that the driver can see that
+    both ran one workload; launch-shape details of the GPU arm live under `launch`."""
+    return {"workload": workload_name(E, frames), "envs_per_gpu": E, "frames_per_step": frames,
+            "l2": "GPU arm: flushed between timed steps (256 MiB write); CPU arm: not applicable",
+            "parallelism": "env-sharded x%d, no collective on the step path" % world}
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path.  The reference is pure Python and cannot
-    travel to the GPU box, so this times its C restatement (oracle/, bit-exact against it) on all host threads."""
+    """--impl reference: the reference's CPU implementation of the path.  The reference is pure Python and cannot travel
+    to the GPU box, so this times its C restatement (oracle/, bit-exact against it) on all host threads, each step a
+    bounded sample of the same workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -139,6 +184,7 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     frames = args.frames
     decisions = frames // PERIOD
+    frames = decisions * PERIOD
     # size one step to ~2 s
     t0 = time.perf_counter()
     steps, _ = orc.rollout_batch(cfg, cores, 11, 0, 10, cores)
@@ -154,21 +200,137 @@ def run_reference(args):
         total += s
     dt = time.perf_counter() - t0
     v = total / dt
-    sample = "%d envs x %d frames per step (bounded sample of the %d-env workload) on %d threads" % (
-        envs, decisions * PERIOD, args.envs, cores)
+    sample = "sample of %d envs x %d frames per step (of the %d-env workload) on %d threads" % (envs, frames, args.envs, cores)
+    conf = base_config(args.envs, frames, max(args.gpus, 1))
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args.envs, frames), "envs_per_gpu": args.envs, "frames_per_step": frames},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": conf,
+            "sample": {"envs": envs, "frames": frames, "of_envs": args.envs, "threads": cores, "text": sample},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "python_reference": python_reference_numbers()},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
 
 
-def workload_name(envs, frames):
-    return ("configs[1]: pellet collection, 1 RL agent, no opponents/viruses, grid-vision obs; %d envs per GPU, "
-            "random-action driver, %d-frame rollouts (frame-skip 7, obs every 8th frame)" % (envs, frames))
+def device_rollouts(batch, decisions, steps, warmup, flush, dist=None, world=1):
+    """W untimed + K timed persistent rollouts (one launch each), L2 flushed between timed steps, CUDA events on the launching
+    stream, max over ranks.  Returns total ms of the K steps."""
+    import torch
+    for i in range(warmup):
+        batch.rollout_random(decisions, PERIOD, decision_base=i * decisions)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    evs = []
+    for i in range(steps):
+        if flush is not None:
+            flush.fill_(i & 0xff)  # evict L2 between timed steps (126 MB L2 < 256 MiB)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        batch.rollout_random(decisions, PERIOD, decision_base=(warmup + i) * decisions)
+        e.record()
+        evs.append((s, e))
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    total_ms = float(sum(s.elapsed_time(e) for s, e in evs))
+    if dist is not None:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=batch.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    return total_ms
+
+
+def scaling_sweep(cfg, local, rank, world, dist, flush):
+    """BASELINE configs[4]: 65 536 / 262 144 / 1 048 576 TOTAL envs sharded evenly over the ranks (shard_envs: contiguous global
+    env ids, Philox key = global id), observations handed to a torch DQN (MLP 123-100-100-25) through DLPack, arg-max -> the
+    reference's 5x5 action table -> 8 frames; one tick = MLP + our step kernel captured in a CUDA graph.  Timed with CUDA
+    events per rank, max over ranks."""
+    import torch
+    from aigar_b200.dqn import DQNDriver
+    from aigar_b200.env import AgarBatch
+    from aigar_b200.sharding import shard_envs
+    peak, _ = measured_peak()
+    out = {}
+    for total in (65536, 262144, 1048576):
+        try:
+            first, n = shard_envs(total, world, rank)
+            b = AgarBatch(cfg, n, device=local, seed=2026, first_env_id=10 ** 7 + first)
+            drv = DQNDriver(b, seed=0)
+            ticks = 12
+            drv.run(4, use_graph=True)
+            if dist is not None:
+                dist.barrier()
+            torch.cuda.synchronize()
+            flush.fill_(1)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(ticks):
+                drv._graph.replay()
+            e.record()
+            torch.cuda.synchronize()
+            ms = s.elapsed_time(e)
+            # the env path alone at the same size (persistent random-action rollout)
+            d2 = 12
+            for i in range(2):
+                b.rollout_random(d2, PERIOD, decision_base=i * d2)
+            torch.cuda.synchronize()
+            flush.fill_(2)
+            s.record()
+            b.rollout_random(d2, PERIOD, decision_base=2 * d2)
+            e.record()
+            torch.cuda.synchronize()
+            ms_env = s.elapsed_time(e)
+            t = torch.tensor([ms, ms_env], dtype=torch.float64, device=b.device)
+            if dist is not None:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, ms_env = float(t[0].item()), float(t[1].item())
+            v = total * ticks * PERIOD / (ms * 1e-3)
+            v_env = total * d2 * PERIOD / (ms_env * 1e-3)
+            out["envs_%d" % total] = {
+                "total_envs": total, "envs_per_gpu": n, "n_gpus": world, "value_dqn_loop": v, "value_env_only": v_env,
+                "unit": UNIT, "ms_per_tick": ms / ticks, "tile_width": b.tile_width,
+                "state_bytes_per_gpu": int(n * b.layout.record_bytes),
+                "roofline_frac_per_gpu_dqn_loop": v / world * algorithmic_bytes_per_env_step() / 1e9 / peak,
+                "roofline_frac_per_gpu_env_only": v_env / world * algorithmic_bytes_per_env_step() / 1e9 / peak}
+            b.close()
+            del drv
+        except Exception as ex:  # never lose the headline line to a side measurement
+            out["envs_%d" % total] = {"error": str(ex)[:200]}
+    return out
+
+
+def other_config(key, local, flush, steps=5, warmup=2, with_cpu=True, e2e_steps=2, groups=2):
+    """BASELINE configs[2] / [3] to the same contract as the headline: full 1000-frame rollouts at the named env count, L2 flush,
+    >= 5 timed steps, their own e2e (host buffers through the C ABI) and CPU baseline (the C port on the host cores)."""
+    import torch
+    import aigar_b200.layout as lay
+    from aigar_b200.env import AgarBatch
+    spec = CONFIGS[key]
+    cfg = lay.derive_config(**spec["kw"])
+    E, decisions = spec["envs"], 1000 // PERIOD
+    frames = decisions * PERIOD
+    peak, _ = measured_peak()
+    b = AgarBatch(cfg, E, device=local, seed=2026, first_env_id=3 * 10 ** 6)
+    n0 = b.launch_count
+    ms = device_rollouts(b, decisions, steps, warmup, flush)
+    v = E * frames * steps / (ms * 1e-3)
+    res = {"workload": workload_name(E, frames, key), "value": v, "unit": UNIT, "steps": steps, "warmup": warmup,
+           "ms_per_step": ms / steps, "frames_per_step": frames, "envs": E, "gpu_launches": int(b.launch_count - n0 - warmup),
+           "bytes_per_env_step": spec["bytes"], "roofline_frac": v * spec["bytes"] / 1e9 / peak,
+           "players": int(b.layout.n_players), "state_len": int(b.layout.state_len), "tile_width": b.tile_width,
+           "record_bytes": int(b.layout.record_bytes), "l2": "flushed between timed steps"}
+    b.close()
+    try:
+        res["e2e"] = run_e2e(cfg, E, decisions, e2e_steps, local, 0, 1, None, torch.cuda.synchronize, groups)
+    except Exception as ex:
+        res["e2e"] = {"error": str(ex)[:200]}
+    if with_cpu:
+        cores = os.cpu_count() or 1
+        cv, sample = cpu_port_throughput(cores, spec["kw"], target_s=6.0)
+        res["cpu_baseline"] = {"value": cv, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+    return res
 
 
 def run_e2e(cfg, E, decisions, e2e_steps, local, rank, world, dist, barrier, groups, seed=2026):
@@ -276,12 +438,12 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
 
-    import numpy as np
     import torch
     import aigar_b200.layout as lay
     from aigar_b200.env import AgarBatch
@@ -296,6 +458,13 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    try:  # one core set per rank: eight ranks polling / launching on one NUMA node otherwise share the same cores
+        ncpu = os.cpu_count() or 1
+        if world > 1 and ncpu >= 2 * world:
+            per = ncpu // world
+            os.sched_setaffinity(0, set(range(local * per, (local + 1) * per)))
+    except Exception:
+        pass
 
     def barrier():
         if dist is not None:
@@ -310,39 +479,19 @@ def main():
     L = batch.layout
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=batch.device)
 
-    def one_step(i):
-        batch.rollout_random(decisions, PERIOD, decision_base=i * decisions)
-
     sampler = ClockSampler(local)  # samples from the warm-up on: the same load, more samples than the timed region alone
     sampler.start()
-    for i in range(args.warmup):
-        one_step(i)
-    barrier()
     launches0 = batch.launch_count
-    evs = []
-    barrier()
-    for i in range(args.steps):
-        flush.fill_(i & 0xff)  # evict L2 between timed steps (126 MB L2 < 256 MiB)
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        one_step(args.warmup + i)
-        e.record()
-        evs.append((s, e))
-    barrier()
-    launches = batch.launch_count - launches0
+    total_ms = device_rollouts(batch, decisions, args.steps, args.warmup, flush, dist, world)
+    launches = batch.launch_count - launches0 - args.warmup
     clocks = sampler.stop()
-    kernel_ms = [s.elapsed_time(e) for s, e in evs]
-    total_ms = float(sum(kernel_ms))
-    t = torch.tensor([total_ms], dtype=torch.float64, device=batch.device)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
     value = world * E * frames * args.steps / (total_ms * 1e-3)
 
     # ---- e2e: host buffers through the C ABI's host-buffer step (actions H2D, obs/reward/done D2H every decision)
     e2e = None
     if not args.no_e2e:
         e2e = run_e2e(cfg, E, decisions, min(args.steps, 5), local, rank, world, dist, barrier, args.groups)
+
     # ---- episode statistics: the one optional collective, outside the timed region
     stats = batch.get(lay.GET_STATS).sum(dim=(0, 1))
     ovf = (batch.get(lay.GET_OVERFLOW) != 0).sum().to(torch.float64)
@@ -351,31 +500,11 @@ def main():
         dist.all_reduce(ovf)
     mean_mass = float(stats[0].item() / max(stats[2].item(), 1.0))
 
-    # ---- extra: the HBM-resident regime (state >> L2), same kernel
     extra = {}
-    if not args.no_extra and rank == 0:
-        try:
-            E2, d2 = 262144, 25
-            b2 = AgarBatch(cfg, E2, device=local, seed=2026, first_env_id=10 ** 6)
-            for i in range(3):
-                b2.rollout_random(d2, PERIOD, decision_base=i * d2)
-            ts = []
-            for i in range(5):
-                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                s.record()
-                b2.rollout_random(d2, PERIOD, decision_base=(3 + i) * d2)
-                e.record()
-                torch.cuda.synchronize()
-                ts.append(s.elapsed_time(e))
-            ms = sum(ts) / len(ts)
-            v2 = E2 * d2 * PERIOD / (ms * 1e-3)
-            peak, _ = measured_peak()
-            extra["envs_262144"] = {"value": v2, "unit": UNIT, "ms_per_launch": ms, "frames_per_launch": d2 * PERIOD,
-                                    "state_bytes": int(E2 * L.record_bytes), "tile_width": b2.tile_width,
-                                    "roofline_frac": v2 * algorithmic_bytes_per_env_step() / 1e9 / peak}
-            b2.close()
-        except Exception as ex:  # never lose the headline line to the side measurement
-            extra["envs_262144"] = {"error": str(ex)[:200]}
+    # ---- BASELINE configs[4]: the env-count sweep sharded over ALL ranks with the DQN consumer (every N)
+    if not args.no_extra and not args.no_sweep:
+        extra["sweep"] = scaling_sweep(cfg, local, rank, world, dist, flush)
+    if not args.no_extra and rank == 0 and world == 1:
         try:  # the same workload with an observation EVERY frame (FRAME_SKIP_RATE = 0 -> 1672 B per env-step)
             cfg0 = lay.derive_config(frame_skip=0)
             b0 = AgarBatch(cfg0, E, device=local, seed=2026, first_env_id=5 * 10 ** 6)
@@ -399,59 +528,12 @@ def main():
             b0.close()
         except Exception as ex:
             extra["obs_every_frame"] = {"error": str(ex)[:200]}
-        # BASELINE configs[2] / [3] (parity-test cases, reported for reference): multi-agent kernels, 96-frame launches
-        # algorithmic bytes per env-step: SURVEY §8d's worked figures for these configs (obs every 8th frame)
-        for name, kw, En, bpe in (("config3_1v1_greedy_16384", dict(num_nn=1, num_greedy=1, virus=True, split=True, eject=True), 16384, 2950.0),
-                                  ("config4_arena_8192", dict(num_nn=8, num_greedy=8, virus=True, split=True, eject=True), 8192, 22900.0)):
+        # BASELINE configs[2] / [3] to the same contract (full rollouts, flush, e2e, CPU arm)
+        for key in ("configs[2]", "configs[3]"):
             try:
-                cm = lay.derive_config(**kw)
-                bm = AgarBatch(cm, En, device=local, seed=2026, first_env_id=3 * 10 ** 6)
-                bm.rollout_random(12, PERIOD, decision_base=0)
-                ts = []
-                for i in range(2):
-                    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    s.record()
-                    bm.rollout_random(12, PERIOD, decision_base=(1 + i) * 12)
-                    e.record()
-                    torch.cuda.synchronize()
-                    ts.append(s.elapsed_time(e))
-                ms = sum(ts) / len(ts)
-                vm = En * 12 * PERIOD / (ms * 1e-3)
-                extra[name] = {"value": vm, "unit": UNIT, "ms_per_launch": ms, "frames_per_launch": 12 * PERIOD,
-                               "bytes_per_env_step": bpe, "roofline_frac": vm * bpe / 1e9 / measured_peak()[0],
-                               "players": int(bm.layout.n_players), "state_len": int(bm.layout.state_len), "tile_width": bm.tile_width}
-                bm.close()
+                extra[key] = other_config(key, local, flush, with_cpu=not args.no_cpu, groups=2)
             except Exception as ex:
-                extra[name] = {"error": str(ex)[:200]}
-        try:  # BASELINE configs[4] shard: obs -> DLPack -> torch DQN forward -> arg-max -> 5x5 table -> 8 frames
-            from aigar_b200.dqn import DQNDriver
-            E3, ticks = 65536, 20
-            b3 = AgarBatch(cfg, E3, device=local, seed=2026, first_env_id=2 * 10 ** 6)
-            drv = DQNDriver(b3, seed=0)
-            drv.run(5)
-            torch.cuda.synchronize()
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            for _ in range(ticks):
-                drv.tick()
-            e.record()
-            torch.cuda.synchronize()
-            ms = s.elapsed_time(e)
-            drv.run(4, use_graph=True)  # capture one tick into a CUDA graph, then time replays
-            torch.cuda.synchronize()
-            s.record()
-            for _ in range(ticks):
-                drv._graph.replay()
-            e.record()
-            torch.cuda.synchronize()
-            ms_g = s.elapsed_time(e)
-            extra["dqn_65536"] = {"value": E3 * ticks * PERIOD / (ms * 1e-3), "unit": UNIT, "ms_per_tick": ms / ticks,
-                                  "value_cuda_graph": E3 * ticks * PERIOD / (ms_g * 1e-3), "ms_per_tick_cuda_graph": ms_g / ticks,
-                                  "policy": "torch MLP 123-100-100-25 (fp32), arg-max, 5x5 action table; obs via DLPack",
-                                  "tile_width": b3.tile_width}
-            b3.close()
-        except Exception as ex:
-            extra["dqn_65536"] = {"error": str(ex)[:200]}
+                extra[key] = {"error": str(ex)[:200]}
         try:  # transitions from the env's buffers into the GPU replay ring, prioritized sampling
             from aigar_b200.replay import GpuReplayBuffer
             E4 = 65536
@@ -498,20 +580,25 @@ def main():
     bytes_per = algorithmic_bytes_per_env_step()
     launch_ms = total_ms / args.steps
     achieved = E * frames * bytes_per / (launch_ms * 1e-3) / 1e9
+    prof = profiled_kernel_facts(E, frames)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": profiled_traffic(E, frames), "kernel": ("k_simple<%d>" if batch.tile_width <= 16 else "k_main<%d,false>") % batch.tile_width, "peak_source": peak_src,
-                "bytes_per_env_step": bytes_per, "env_steps_per_launch": E * frames, "launch_ms": launch_ms}
+                "traffic": prof.get("dram_bytes_per_launch"), "kernel": ("k_simple<%d>" if batch.tile_width <= 16 else "k_main<%d,false>") % batch.tile_width, "peak_source": peak_src,
+                "bytes_per_env_step": bytes_per, "env_steps_per_launch": E * frames, "launch_ms": launch_ms,
+                # the persistent launch keeps an env on chip for the whole rollout: real DRAM traffic is ~0.1 % of the algorithmic
+                # bytes and the kernel is issue / latency bound — the numbers that say how busy the SMs are (ncu, profiles/):
+                "real_dram_bytes_per_env_step": prof.get("dram_bytes_per_env_step"),
+                "issue_slots_busy_pct": prof.get("issue_active_pct"), "warp_instructions_per_env_step": prof.get("warp_inst_per_env_step"),
+                "profile": prof.get("source")}
     cpu = None
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
         v, sample = cpu_port_throughput(cores)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+               "python_reference": python_reference_numbers()}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": launch_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": workload_name(E, frames), "envs_per_gpu": E, "frames_per_step": frames,
-                       "l2": "flushed between timed steps (256 MiB write)", "tile_width": batch.tile_width,
-                       "record_bytes": int(L.record_bytes), "parallelism": "env-sharded x%d, no collective on the step path" % world},
+            "data": "synthetic", "config": base_config(E, frames, world),
+            "launch": {"tile_width": batch.tile_width, "record_bytes": int(L.record_bytes), "kernel": roofline["kernel"]},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "episode_stats": {"mean_mass": mean_mass, "envs_with_pool_overflow": int(ovf.item())}, "extra": extra}
     print(json.dumps(line))
