@@ -123,15 +123,6 @@ __global__ void k_rp_store(ReplayDev d, const float* __restrict__ obs_t, const f
         }
     }
 }
-/* all nodes of one tree level: value[node] = op(value[2 node], value[2 node + 1]) (segment_tree.py:76-87) */
-__global__ void k_rp_level(ReplayDev d, int first, int count) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    int node = first + i;
-    d.sum[node] = d.sum[2 * node] + d.sum[2 * node + 1];
-    double a = d.mn[2 * node], b = d.mn[2 * node + 1];
-    d.mn[node] = b < a ? b : a; /* Python min(a, b): b only if b < a */
-}
 __global__ void k_rp_init(ReplayDev d) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < 2 * d.itcap) {
@@ -260,11 +251,29 @@ __global__ void k_rp_max_priority(ReplayDev d, const double* __restrict__ prio, 
     *d.max_priority = m;
 }
 
-static int rp_rebuild(AgarReplay* rp, cudaStream_t s) {
-    for (int count = rp->d.itcap / 2; count >= 1; count /= 2) {
-        k_rp_level<<<(count + 255) / 256, 256, 0, s>>>(rp->d, count, count);
-        rp->launches += 1;
+/* Repair the sum / min trees above the n leaves idx[0..n) (entries < 0 are skipped) in ONE launch: a node is
+ * op(left child, right child) (segment_tree.py:76-87), so only the ancestors of touched leaves change, level by level.  One
+ * CTA walks the levels with a barrier in between; threads that reach the same parent recompute the same value from the same
+ * finished children (a benign duplicate).  Replaces 20 level-wide launches per add / priority update (the learner tick is
+ * launch-bound: ~150 small kernels). */
+__global__ void __launch_bounds__(1024) k_rp_fix_paths(ReplayDev d, const int32_t* __restrict__ idx, int n) {
+    int levels = 0;
+    while ((1 << levels) < d.itcap) ++levels;
+    for (int lv = 1; lv <= levels; ++lv) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int p = idx[i];
+            if (p < 0 || p >= d.cap) continue;
+            const int node = (d.itcap + p) >> lv;
+            d.sum[node] = d.sum[2 * node] + d.sum[2 * node + 1];
+            const double a = d.mn[2 * node], b = d.mn[2 * node + 1];
+            d.mn[node] = b < a ? b : a; /* Python min(a, b): b only if b < a */
+        }
+        __syncthreads();
     }
+}
+static int rp_fix_paths(AgarReplay* rp, const int32_t* idx_dev, int n, cudaStream_t s) {
+    k_rp_fix_paths<<<1, 1024, 0, s>>>(rp->d, idx_dev, n);
+    rp->launches += 1;
     RCU(cudaGetLastError());
     return AGAR_OK;
 }
@@ -337,7 +346,7 @@ extern "C" int agar_replay_add_batch(AgarReplay* rp, const float* obs_t, const f
     k_rp_store<<<(int)(((size_t)n * 32 + 255) / 256), 256, 0, s>>>(rp->d, obs_t, action, reward, obs_tp1, done, n);
     RCU(cudaGetLastError());
     rp->launches += 2;
-    if (rp->d.prioritized) return rp_rebuild(rp, s);
+    if (rp->d.prioritized) return rp_fix_paths(rp, rp->d.pos, n, s);
     return AGAR_OK;
 }
 extern "C" int agar_replay_gather(AgarReplay* rp, const int32_t* idx_dev, int batch, float* obs_t, float* action, float* reward,
@@ -383,5 +392,5 @@ extern "C" int agar_replay_update_priorities(AgarReplay* rp, const int32_t* idx_
     k_rp_max_priority<<<1, 1, 0, s>>>(rp->d, priorities_dev, batch);
     RCU(cudaGetLastError());
     rp->launches += 2;
-    return rp_rebuild(rp, s);
+    return rp_fix_paths(rp, idx_dev, batch, s);
 }

@@ -23,7 +23,10 @@ def main():
     ap.add_argument("--ticks", type=int, default=3000)
     ap.add_argument("--batch", type=int, default=2048)
     ap.add_argument("--reset-every", type=int, default=250)  # RESET_LIMIT / 8 in the reference is 2500 ticks; shorter here
+    ap.add_argument("--no-graph", action="store_true", help="the round-1 loop: one launch per op, a host sync per tick")
     args = ap.parse_args()
+    if not args.no_graph:
+        return main_graphed(args)
     cfg = lay.derive_config()
     env = AgarBatch(cfg, args.envs, seed=1)
     L = env.layout.state_len
@@ -54,6 +57,37 @@ def main():
             env.reset()
             env.reset_bots()
             obs = env.observe().clone()
+
+
+def main_graphed(args):
+    """The same run with the whole tick (decide -> step -> replay add -> PER sample -> TD step -> priorities) replayed as one
+    CUDA graph (aigar_b200.learner.GraphedDQNLoop): no launch overhead, no host synchronisation inside a tick."""
+    from aigar_b200.learner import GraphedDQNLoop
+    cfg = lay.derive_config()
+    env = AgarBatch(cfg, args.envs, seed=1)
+    L = env.layout.state_len
+    net = make_dqn(L, device=env.device, seed=0)
+    rp = GpuReplayBuffer(1 << 20, L, 1, prioritized=True, alpha=0.6, beta=0.4)
+    loop = GraphedDQNLoop(env, net, rp, batch_size=args.batch, eps_decay_ticks=0.6 * args.ticks)
+    env.observe()
+    torch.cuda.synchronize()
+    t0 = t_prev = time.time()
+    done = 0
+    while done < args.ticks:
+        n = min(args.reset_every, args.ticks - done)
+        n = loop.run(n)
+        done += n
+        mass = env.get(lay.GET_MASS).mean().item()  # the only host synchronisation: once per reporting interval
+        eps = max(0.05, 1.0 - done / (0.6 * args.ticks) * 0.95)
+        now = time.time()
+        print("tick %5d  eps %.2f  mean mass after %d frames %.1f  loss %.3f  (%.3g env-steps/s incl. learning in this interval, "
+              "%.3g since start incl. graph capture)" % (done, eps, n * 8, mass, float(loop.loss), args.envs * n * 8 / (now - t_prev),
+                                                         args.envs * done * 8 / (now - t0)), flush=True)
+        t_prev = time.time()
+        env.reset()
+        env.reset_bots()
+        env.observe()
+    rp.raise_on_error()
 
 
 if __name__ == "__main__":

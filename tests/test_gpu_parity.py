@@ -524,3 +524,28 @@ def test_multi_agent_results_do_not_depend_on_launch_shape(torch_cuda, kw, n_env
     for b in [whole] + parts:
         b.rollout_random(40, 8, 0)
     assert torch.equal(whole.state_tensor(), torch.cat([p.state_tensor() for p in parts], 0))
+
+
+def test_graphed_dqn_loop(torch_cuda):
+    """The collector + trainer tick as one CUDA graph (aigar_b200.learner.GraphedDQNLoop): the envs advance exactly as with
+    explicit calls (frame counters), the replay buffer fills with one transition per env and tick, the TD loss is finite and
+    the networks move."""
+    torch = torch_cuda
+    from aigar_b200.dqn import make_dqn
+    from aigar_b200.learner import GraphedDQNLoop
+    from aigar_b200.replay import GpuReplayBuffer
+    cfg = lay.derive_config()
+    E = 256
+    env = _batch(cfg, E, seed=12)
+    net = make_dqn(env.layout.state_len, device=env.device, seed=0)
+    w0 = [p.detach().clone() for p in net.parameters()]
+    rp = GpuReplayBuffer(1 << 14, env.layout.state_len, 1, prioritized=True)
+    loop = GraphedDQNLoop(env, net, rp, batch_size=128, eps_decay_ticks=20, learn_after=4)
+    env.observe()
+    done = loop.run(40)
+    torch.cuda.synchronize()
+    assert done >= 40 and rp.error_flags == 0
+    stats = env.get(lay.GET_STATS).cpu().numpy()
+    assert (stats[:, 0, 2] == done * 8 + 1).all()             # 8 frames per tick (+ the bot turn of the first observation)
+    assert len(rp) == min(1 << 14, done * E)                  # one transition per env and tick
+    assert np.isfinite(float(loop.loss)) and any(not torch.equal(a, b) for a, b in zip(w0, net.parameters()))
