@@ -1106,6 +1106,8 @@ DEV bool cell_eats_pellets_indexed(Ctx<W>& c, const DevParams& P, int k, int ci,
         m_max = cm + 3.0 * total;
         if (!(m_max < AG_MAX_MASS)) m_max = AG_MAX_MASS;
         r_max = radius_of(m_max);
+        if (r_max < cr) r_max = cr; /* after an eject the stored radius is STALE (larger than sqrt(mass / pi), cell.py:92) until the
+                                     * next decay; the first tests of the chain use it as it is */
         if ((int)r_max + 2 <= R) break;
         R = (int)r_max + 2;
     }

@@ -271,9 +271,27 @@ __global__ void __launch_bounds__(1024) k_rp_fix_paths(ReplayDev d, const int32_
         __syncthreads();
     }
 }
+/* all nodes of one tree level: value[node] = op(value[2 node], value[2 node + 1]) (segment_tree.py:76-87) */
+__global__ void k_rp_level(ReplayDev d, int first, int count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    int node = first + i;
+    d.sum[node] = d.sum[2 * node] + d.sum[2 * node + 1];
+    double a = d.mn[2 * node], b = d.mn[2 * node + 1];
+    d.mn[node] = b < a ? b : a;
+}
+/* few touched leaves (a learner's batch, a tick of a few thousand envs): one launch that walks their ancestors; many (a tick of
+ * 65k envs touches a large part of every level anyway): one grid-wide launch per level */
 static int rp_fix_paths(AgarReplay* rp, const int32_t* idx_dev, int n, cudaStream_t s) {
-    k_rp_fix_paths<<<1, 1024, 0, s>>>(rp->d, idx_dev, n);
-    rp->launches += 1;
+    if (n <= 8192) {
+        k_rp_fix_paths<<<1, 1024, 0, s>>>(rp->d, idx_dev, n);
+        rp->launches += 1;
+    } else {
+        for (int count = rp->d.itcap / 2; count >= 1; count /= 2) {
+            k_rp_level<<<(count + 255) / 256, 256, 0, s>>>(rp->d, count, count);
+            rp->launches += 1;
+        }
+    }
     RCU(cudaGetLastError());
     return AGAR_OK;
 }

@@ -564,7 +564,7 @@ def main():
             bytes_tr = (2 * L.state_len + 4 + 1) * 4 + 1
             extra["replay"] = {"add_transitions_per_s": E4 / (add_ms * 1e-3), "add_gbs": 2 * E4 * bytes_tr / (add_ms * 1e-3) / 1e9,
                                "per_sample_4096_ms": smp_ms, "capacity": 1 << 20, "prioritized": True,
-                               "note": "add = block scan + one warp per transition + one tree-repair launch; GB/s counts read + write"}
+                               "note": "add = block scan + one warp per transition + tree repair (20 level launches at this batch size); GB/s counts read + write"}
             b4.close(), rp.close()
         except Exception as ex:
             extra["replay"] = {"error": str(ex)[:200]}
