@@ -552,3 +552,12 @@ def test_graphed_dqn_loop(torch_cuda):
     assert (stats[:, 0, 2] == done * 8 + 1).all()             # 8 frames per tick (+ the bot turn of the first observation)
     assert len(rp) == min(1 << 14, done * E)                  # one transition per env and tick
     assert np.isfinite(float(loop.loss)) and any(not torch.equal(a, b) for a, b in zip(w0, net.parameters()))
+
+
+@pytest.mark.parametrize("case", [0, 1, 2])
+def test_fast_paths_equal_sequential_shape_and_oracle_at_steady_state(torch_cuda, case):
+    """tools/gpu_shape_stress.py: 200 envs x 1200 frames of a split / eject / merge-heavy multi-agent config, 32-lane tiles (per-env
+    pellet index, cooperative self-collision sweep, cooperative player-player pass) against 16-lane tiles (the sequential lane-0
+    forms, direct pool scans) — identical records every 200 frames — and three envs against the CPU oracle at the end."""
+    import gpu_shape_stress
+    assert gpu_shape_stress.run(1200, 200, cases=(case,))
