@@ -604,7 +604,7 @@ DEV void update_viruses_blobs(Ctx<W>& c, const DevParams& P) {
 
 /* lane 0: split / eject flag / movement / ejections / collisions of one player.  vel = scratch [cells][2]. */
 template <int W>
-DEVN void player_rare_path(Ctx<W>& c, const DevParams& P, int k, double* vel) {
+DEVN void player_split_and_flags(Ctx<W>& c, const DevParams& P, int k, double* vel) { /* lane 0; before the cells move */
     AgarPlayer* p = &c.pl[k];
     AgarCell* base = CELLP(c, P, k, 0);
     const double S = (double)P.S;
@@ -645,10 +645,14 @@ DEVN void player_rare_path(Ctx<W>& c, const DevParams& P, int k, double* vel) {
     if (p->do_eject) /* player.py:63-68 */
         for (int i = 0; i < p->n_cells; ++i)
             if (base[i].mass >= 35) base[i].flags |= AGAR_CF_EJECT;
-    for (int i = 0; i < p->n_cells; ++i) { /* updateCellsMovement */
-        AgarCell* q = &base[i];
-        update_pos(q->x, q->y, vx[i], vy[i], q->svx, q->svy, q->counter, S);
-    }
+}
+
+/* lane 0; after the player's cells have moved, before their self-collisions (field.py:134-146) */
+template <int W>
+DEVN void player_ejections(Ctx<W>& c, const DevParams& P, int k) {
+    AgarPlayer* p = &c.pl[k];
+    AgarCell* base = CELLP(c, P, k, 0);
+    const double S = (double)P.S;
     if (p->do_eject) /* field.py:134-146, cell.py:90-94 */
         for (int i = 0; i < p->n_cells; ++i) {
             AgarCell* q = &base[i];
@@ -842,22 +846,37 @@ DEV void update_players(Ctx<W>& c, const DevParams& P) {
         vel[(size_t)k * cap * 2 + cap + i] = vy;
     }
     c.t.sync();
-    /* phase B: per player, in player order (events and the blob list are ordered by player) */
+    /* phase B (updatePlayers, field.py:112-119 + player.py:30-36), per player in player order: split, eject flags, move the cells,
+     * eject, push overlapping cells apart.  Nothing of it reads another player's cells, so the steps that are independent per CELL
+     * run for all players at once — B1 (lane 0, rare: only on decision frames with a split / eject bit): splits and eject flags;
+     * B2 (one lane per cell): every live cell moves; B3 (player order): ejections on lane 0 (the blob list is ordered by player),
+     * then the cooperative self-collision sweep.  (Round 1 moved the cells of one player after the other on lane 0: in the arena,
+     * whose cells live in HBM, that was a chain of ~50 dependent global round trips per frame.) */
     for (int k = 0; k < K; ++k) {
         AgarPlayer* p = &c.pl[k];
         if (!p->alive) {
             if (c.lane == 0) p->respawn_time -= 1;
             continue;
         }
-        bool rare = p->do_split || p->do_eject || p->n_cells > 1;
-        if (rare) {
-            if (c.lane == 0) player_rare_path(c, P, k, vel);
-            c.t.sync(); /* positions (and a split's new cells) are visible to the tile */
-            player_self_collisions<W>(c, P, k);
-        } else if (c.lane == 0) {
-            AgarCell* q = CELLP(c, P, k, 0);
-            update_pos(q->x, q->y, vel[(size_t)k * cap * 2], vel[(size_t)k * cap * 2 + cap], q->svx, q->svy, q->counter, S);
+        if ((p->do_split || p->do_eject) && c.lane == 0) player_split_and_flags(c, P, k, vel);
+    }
+    c.t.sync();
+    for (int idx = c.lane; idx < K * cap; idx += W) {
+        int k = idx / cap, i = idx - k * cap;
+        const AgarPlayer* p = &c.pl[k];
+        if (!p->alive || i >= p->n_cells) continue;
+        AgarCell* q = CELLP(c, P, k, i);
+        update_pos(q->x, q->y, vel[(size_t)k * cap * 2 + i], vel[(size_t)k * cap * 2 + cap + i], q->svx, q->svy, q->counter, S);
+    }
+    c.t.sync();
+    for (int k = 0; k < K; ++k) {
+        AgarPlayer* p = &c.pl[k];
+        if (!p->alive) continue;
+        if (p->do_eject) {
+            if (c.lane == 0) player_ejections(c, P, k);
+            c.t.sync();
         }
+        if (p->n_cells > 1) player_self_collisions<W>(c, P, k);
     }
     c.t.sync();
     /* updateHashTables: every live cell / virus is (re)inserted */
