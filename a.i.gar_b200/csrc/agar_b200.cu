@@ -655,7 +655,7 @@ extern "C" int agar_create(const AgarConfig* cfg, int n_envs, int device, uint64
      * and before the next bot phase (observation tables dead); pools of <= 8 chunks are scanned directly */
     P.pel_index = e->full && L.pellet_cap > 256 && !(getenv("AGAR_PEL_INDEX") && atoi(getenv("AGAR_PEL_INDEX")) == 0);
     const int gb_idx = (P.S + 9) / 10; /* AG_IDX_CELL */
-    int idx_bytes = P.pel_index ? ((gb_idx * gb_idx + 3) & ~1) * 2 + L.pellet_cap * 2 + 128 + 16 : 0;
+    int idx_bytes = P.pel_index ? ((gb_idx * gb_idx + 3) & ~1) * 2 + L.pellet_cap * 2 + 128 + 64 + 16 : 0; /* counters, entries, sort list, ex-blob list */
     if (idx_bytes > vel_bytes) vel_bytes = idx_bytes;
     P.scratch_bytes = ((vel_bytes > obs_bytes ? vel_bytes : obs_bytes) + 15) / 16 * 16 + 8;
     P.live_off = P.scratch_bytes; /* live-cell list: uint16 per cell slot, after the observation / velocity scratch */

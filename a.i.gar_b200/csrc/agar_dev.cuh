@@ -1181,6 +1181,61 @@ DEV bool cell_eats_pellets_indexed(Ctx<W>& c, const DevParams& P, int k, int ci,
     return true;
 }
 
+/* ONE LANE, one cell: can this cell eat anything this frame?  Conservative (a superset of what the exact ordered chain can eat):
+ * the window / largest-radius bound of cell_eats_pellets_indexed, with every live ex-blob pellet counted into the mass bound.
+ * Used to pre-filter 32 cells at a time: most cells of a frame have no edible pellet in reach and skip the cooperative pass. */
+template <int W>
+DEV bool cell_may_eat(const Ctx<W>& c, const DevParams& P, int k, int ci, const uint16_t* fatlist, int n_fatl, bool fat_unknown) {
+    const int gb = pel_index_gb(P), nc = pel_index_cnt_len(P);
+    const uint16_t* cnt = (const uint16_t*)c.scratch;
+    const uint16_t* ent = cnt + nc;
+    const AgarCell* q = CELLP(c, P, k, ci);
+    const double cx = q->x, cy = q->y, cm = q->mass, cr = q->radius;
+    if (fat_unknown) return true;
+    const Rect rc = rect_of(P.S, cx, cy, cr);
+    const double fat_mass = (double)n_fatl * P.blob_mass * 1.000001;
+    int R = (int)cr + 2, bx0, bx1, by0, by1;
+    double m_max, r_max;
+    for (int pass = 0;; ++pass) {
+        if (pass == 4) return true;
+        const int fx = (int)floor(cx), fy = (int)floor(cy);
+        bx0 = fx - R < 0 ? 0 : (fx - R) / AG_IDX_CELL, bx1 = min(gb - 1, (fx + R + 1) / AG_IDX_CELL);
+        by0 = fy - R < 0 ? 0 : (fy - R) / AG_IDX_CELL, by1 = min(gb - 1, (fy + R + 1) / AG_IDX_CELL);
+        int total = 0;
+        for (int by = by0; by <= by1; ++by) {
+            const int b0 = by * gb + bx0, b1 = by * gb + bx1;
+            total += (int)cnt[b1] - (b0 ? (int)cnt[b0 - 1] : 0);
+        }
+        m_max = cm + 3.0 * total + fat_mass;
+        if (!(m_max < AG_MAX_MASS)) m_max = AG_MAX_MASS;
+        r_max = radius_of(m_max);
+        if (r_max < cr) r_max = cr;
+        if ((int)r_max + 2 <= R) break;
+        R = (int)r_max + 2;
+    }
+    const double rr = (r_max > 1.0 ? r_max * r_max : 1.0) * (1.0 + 1e-9);
+    for (int by = by0; by <= by1; ++by) {
+        const int b0 = by * gb + bx0, b1 = by * gb + bx1;
+        const int beg = b0 ? (int)cnt[b0 - 1] : 0, end = (int)cnt[b1];
+        for (int e = beg; e < end; ++e) {
+            const uint32_t pk = c.pel[ent[e]];
+            if (!pk) continue;
+            const int px = AGAR_PELLET_X(pk), py = AGAR_PELLET_Y(pk), pm = AGAR_PELLET_M(pk);
+            const double dx = cx - (double)px, dy = cy - (double)py;
+            if ((dx * dx + dy * dy) * 1.1 < rr && m_max > 1.25 * (double)pm && rect_hit(rc, pellet_rect(px, py))) return true;
+        }
+    }
+    for (int t = 0; t < n_fatl; ++t) {
+        const AgarFatPellet* f = &c.fat[fatlist[t]];
+        const double fm = f->mass, fr = f->radius;
+        if (fm == 0) continue;
+        const double dx = cx - f->x, dy = cy - f->y;
+        const double reach2 = (fr * fr > rr ? fr * fr * (1.0 + 1e-9) : rr);
+        if ((dx * dx + dy * dy) * 1.1 < reach2 && m_max > 1.25 * fm && rect_hit(rc, rect_of(P.S, f->x, f->y, fr))) return true;
+    }
+    return false;
+}
+
 /* cooperative: the hot loop.  field.py:207-213 + eatPellet :327-344.  For one cell (k, ci): integer pellets in slot
  * order, then float ("fat") pellets in slot order; the eat chain is sequential — a pellet is tested against the
  * cell as grown by every earlier eat — but hits are found 32 pellets at a time with a ballot. */
@@ -1463,10 +1518,43 @@ DEV void field_update_phase(Ctx<W>& c, const DevParams& P, int phase) {
         } else {
             bool fat_too = P.L.fat_cap > 0;
             const bool indexed = W == 32 && pel_index_enabled(P);
-            if (indexed) build_pellet_index(c, P);
-            for (int k = 0; k < P.L.n_players; ++k) {
-                if (!c.pl[k].alive) continue;
-                for (int ci = 0; ci < c.pl[k].n_cells; ++ci) cell_eats_pellets(c, P, k, ci, fat_too && c.h->n_fat > 0, indexed);
+            if (indexed) { /* index + a lane-per-cell pre-filter: only cells that may eat something run the cooperative ordered pass */
+                build_pellet_index(c, P);
+                build_live_cells(c, P);
+                const uint16_t* live = live_cells(c, P);
+                const int cap_c = P.L.cell_cap, n_live = c.n_live;
+                uint16_t* fatlist = (uint16_t*)c.scratch + pel_index_cnt_len(P) + P.L.pellet_cap + 64;
+                int n_fatl = 0;
+                if (fat_too && c.h->n_fat > 0) { /* compact list of the live ex-blob pellets (few) */
+                    for (int base = 0; base < P.L.fat_cap; base += W) {
+                        const int sl = base + c.lane;
+                        const bool on = sl < P.L.fat_cap && c.fat[sl].mass != 0;
+                        const unsigned bal = c.t.ballot(on);
+                        const int pos = n_fatl + __popc(bal & ((1u << c.lane) - 1u));
+                        if (on && pos < 32) fatlist[pos] = (uint16_t)sl;
+                        n_fatl += __popc(bal);
+                    }
+                    c.t.sync();
+                }
+                const bool fat_unknown = n_fatl > 32;
+                for (int base = 0; base < n_live; base += W) {
+                    const int t = base + c.lane;
+                    const int idx = t < n_live ? (int)live[t] : 0;
+                    const bool may = t < n_live && cell_may_eat(c, P, idx / cap_c, idx % cap_c, fatlist, fat_unknown ? 0 : n_fatl, fat_unknown);
+                    unsigned todo = c.t.ballot(may);
+                    while (todo) { /* canonical order: ascending (player, cell) */
+                        const int l = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        const int id = c.t.shfl(idx, l);
+                        cell_eats_pellets(c, P, id / cap_c, id % cap_c, fat_too && c.h->n_fat > 0, true);
+                    }
+                }
+                c.n_live = -1;
+            } else {
+                for (int k = 0; k < P.L.n_players; ++k) {
+                    if (!c.pl[k].alive) continue;
+                    for (int ci = 0; ci < c.pl[k].n_cells; ++ci) cell_eats_pellets(c, P, k, ci, fat_too && c.h->n_fat > 0, false);
+                }
             }
         }
     } else {
