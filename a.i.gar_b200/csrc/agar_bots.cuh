@@ -322,6 +322,27 @@ DEV void observe_agent(Ctx<W>& c, const DevParams& P, int k, int agent, float* o
         /* ---- SELF then ENEMY: biggest cell mass per square; max commutes and positive doubles order like their bit
          * patterns.  Own cells need no hash lookup (bot.py:344), enemies come through the player table (field.py:437-439). */
         const int K = P.L.n_players, cap = P.L.cell_cap;
+        double biggest = 0.0; /* NORMALIZE_GRID_BY_MAX_MASS (bot.py:364-367): mass of the biggest player cell in view, own or enemy */
+        if (cf.normalize_grid_by_max_mass) {
+            const uint16_t* live = live_cells(c, P);
+            const int n_it = c.n_live >= 0 ? c.n_live : K * cap;
+            for (int t = c.lane; t < n_it; t += W) {
+                int idx = c.n_live >= 0 ? (int)live[t] : t;
+                int k2 = idx / cap, j = idx - k2 * cap;
+                if (j >= c.pl[k2].n_cells) continue;
+                const AgarCell* o = CELLP(c, P, k2, j);
+                if (k2 == k) {
+                    if (!in_fov(o->x, o->y, o->radius, fx, fy, fov)) continue;
+                } else if (!(o->flags & AGAR_CF_INHASH) || !rect_hit(ra, rect_of(P.S, o->x, o->y, o->radius)) ||
+                           !in_fov(o->x, o->y, o->radius, fx, fy, fov))
+                    continue;
+                if (o->mass > biggest) biggest = o->mass;
+            }
+            for (int off = W / 2; off > 0; off >>= 1) { /* max over the tile: positive doubles, any order */
+                const double other = c.t.shfl_xor(biggest, off);
+                if (other > biggest) biggest = other;
+            }
+        }
         for (int pass = 0; pass < 3; ++pass) { /* 0: own cells, 1: enemy cells, 2: ALL_PLAYER_GRID (both, bot.py:348-351) */
             const bool own = pass == 0, all = pass == 2;
             const int ch_now = all ? ch_all : (own ? ch_self : ch_enemy), ch_slf = all ? -1 : (own ? ch_self_slf : ch_enemy_slf),
@@ -351,6 +372,7 @@ DEV void observe_agent(Ctx<W>& c, const DevParams& P, int k, int agent, float* o
             float* h_slf = hist ? hist + (own ? 1 : 3) * GG : nullptr; /* the one before */
             for (int idx = c.lane; idx < GG; idx += W) {
                 double v = inside(idx) ? sc.tab[idx] : 0.0; /* 0 bits == 0.0: empty square */
+                if (cf.normalize_grid_by_max_mass && v != 0.0) v = v / biggest; /* bot.py:412,422,430 */
                 if (obs && ch_now >= 0) obs[ch_now * GG + idx] = (float)v;
                 if (ch_slf >= 0) {
                     if (obs) obs[ch_slf * GG + idx] = h_slf[idx];

@@ -846,37 +846,33 @@ DEV void update_players(Ctx<W>& c, const DevParams& P) {
         vel[(size_t)k * cap * 2 + cap + i] = vy;
     }
     c.t.sync();
-    /* phase B (updatePlayers, field.py:112-119 + player.py:30-36), per player in player order: split, eject flags, move the cells,
-     * eject, push overlapping cells apart.  Nothing of it reads another player's cells, so the steps that are independent per CELL
-     * run for all players at once — B1 (lane 0, rare: only on decision frames with a split / eject bit): splits and eject flags;
-     * B2 (one lane per cell): every live cell moves; B3 (player order): ejections on lane 0 (the blob list is ordered by player),
-     * then the cooperative self-collision sweep.  (Round 1 moved the cells of one player after the other on lane 0: in the arena,
-     * whose cells live in HBM, that was a chain of ~50 dependent global round trips per frame.) */
+    /* phase B (updatePlayers, field.py:112-119 + player.py:30-36), per player in player order — the event log and the blob list are
+     * ordered by player: split and eject flags (lane 0, rare: only on decision frames with a split / eject bit), then the player's
+     * cells move, ONE LANE PER CELL (round 1 moved them one after the other on lane 0: in the arena, whose cells live in HBM, a
+     * chain of dependent global round trips), then ejections (lane 0), then the cooperative self-collision sweep. */
     for (int k = 0; k < K; ++k) {
         AgarPlayer* p = &c.pl[k];
         if (!p->alive) {
             if (c.lane == 0) p->respawn_time -= 1;
             continue;
         }
-        if ((p->do_split || p->do_eject) && c.lane == 0) player_split_and_flags(c, P, k, vel);
-    }
-    c.t.sync();
-    for (int idx = c.lane; idx < K * cap; idx += W) {
-        int k = idx / cap, i = idx - k * cap;
-        const AgarPlayer* p = &c.pl[k];
-        if (!p->alive || i >= p->n_cells) continue;
-        AgarCell* q = CELLP(c, P, k, i);
-        update_pos(q->x, q->y, vel[(size_t)k * cap * 2 + i], vel[(size_t)k * cap * 2 + cap + i], q->svx, q->svy, q->counter, S);
-    }
-    c.t.sync();
-    for (int k = 0; k < K; ++k) {
-        AgarPlayer* p = &c.pl[k];
-        if (!p->alive) continue;
-        if (p->do_eject) {
-            if (c.lane == 0) player_ejections(c, P, k);
+        if (p->do_split || p->do_eject) {
+            if (c.lane == 0) player_split_and_flags(c, P, k, vel);
             c.t.sync();
         }
-        if (p->n_cells > 1) player_self_collisions<W>(c, P, k);
+        const int n = p->n_cells;
+        for (int i = c.lane; i < n; i += W) {
+            AgarCell* q = CELLP(c, P, k, i);
+            update_pos(q->x, q->y, vel[(size_t)k * cap * 2 + i], vel[(size_t)k * cap * 2 + cap + i], q->svx, q->svy, q->counter, S);
+        }
+        if (p->do_eject) {
+            c.t.sync();
+            if (c.lane == 0) player_ejections(c, P, k);
+        }
+        if (n > 1) {
+            c.t.sync();
+            player_self_collisions<W>(c, P, k);
+        }
     }
     c.t.sync();
     /* updateHashTables: every live cell / virus is (re)inserted */

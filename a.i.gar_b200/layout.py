@@ -42,7 +42,8 @@ class AgarConfig(ctypes.Structure):
         ("mass_as_reward", ctypes.c_int32), ("obs_mode", ctypes.c_int32),
         ("fat_cap", ctypes.c_int32), ("virus_cap", ctypes.c_int32), ("blob_cap", ctypes.c_int32),
         ("event_cap", ctypes.c_int32),
-        ("pellet_cap", ctypes.c_int32), ("all_player_grid", ctypes.c_int32), ("reserved", ctypes.c_int32 * 5),
+        ("pellet_cap", ctypes.c_int32), ("all_player_grid", ctypes.c_int32), ("normalize_grid_by_max_mass", ctypes.c_int32),
+        ("reserved", ctypes.c_int32 * 4),
         ("reward_scale", ctypes.c_double), ("reward_term", ctypes.c_double),
         ("death_term", ctypes.c_double), ("death_factor", ctypes.c_double),
     ]

@@ -74,7 +74,11 @@ typedef struct AgarConfig {
     int32_t pellet_cap;                   /* integer-pellet slots; 0 = default (the refill target, field.py:65) */
     int32_t all_player_grid;              /* ALL_PLAYER_GRID :88-91 — one channel with the biggest cell of ANY player per square,
                                            * instead of the self / enemy channels (which must then be off)      */
-    int32_t reserved[5];
+    int32_t normalize_grid_by_max_mass;   /* NORMALIZE_GRID_BY_MAX_MASS :76-77 as the RUN's parameters module carries it (bot.py:365,412,
+                                           * 422,430): the own / enemy / all-player channels are divided by the mass of the biggest
+                                           * player cell in view.  (bot.py:402,439 — pellet and virus channels — read the package-
+                                           * global flag instead, which the reference's driver never rewrites: not modelled.)      */
+    int32_t reserved[4];
     double reward_scale;                  /* REWARD_SCALE :70 */
     double reward_term;                   /* REWARD_TERM  :69 */
     double death_term;                    /* DEATH_TERM   :71 */

@@ -932,6 +932,7 @@ static void observe_agent(OracleEnv* e, int k, int agent, float* obs, double* ob
         if (!rect_hit(ra, rect_of(e, f->x, f->y, f->radius)) || !in_fov(f->x, f->y, f->radius, fx, fy, fov)) continue;
         grid_insert(&g, T_PELLET, f->x, f->y, f->radius, f->mass, left, top, fov, gs);
     }
+    double biggest = 0.0; /* bot.py:364-367: mass of the biggest player cell in view (own or enemy), NORMALIZE_GRID_BY_MAX_MASS */
     for (int k2 = 0; k2 < e->L.n_players; ++k2) /* getEnemyPlayerCellsInFov (through the player table) */
         for (int j = 0; j < e->pl[k2].n_cells; ++j) {
             const AgarCell* o = CELLP(e, k2, j);
@@ -940,11 +941,13 @@ static void observe_agent(OracleEnv* e, int k, int agent, float* obs, double* ob
                 !in_fov(o->x, o->y, o->radius, fx, fy, fov))
                 continue;
             grid_insert(&g, T_ENEMY, o->x, o->y, o->radius, o->mass, left, top, fov, gs);
+            if (o->mass > biggest) biggest = o->mass;
         }
     for (int j = 0; j < p->n_cells; ++j) { /* own cells: getPortionOfCellsInFov(player.getCells()) */
         const AgarCell* o = CELLP(e, k, j);
         if (!in_fov(o->x, o->y, o->radius, fx, fy, fov)) continue;
         grid_insert(&g, T_OWN, o->x, o->y, o->radius, o->mass, left, top, fov, gs);
+        if (o->mass > biggest) biggest = o->mass;
     }
     if (cf->virus_enabled)
         for (int v = 0; v < e->h->n_viruses; ++v) {
@@ -963,8 +966,8 @@ static void observe_agent(OracleEnv* e, int k, int agent, float* obs, double* ob
             int count = r + c * G;
             if (!(midx + gs / 2 < 0 || midx - gs / 2 > S || midy + gs / 2 < 0 || midy - gs / 2 > S)) {
                 if (g.pel_has[count]) pel[count] = g.pel_sum[count];
-                if (g.enemy_has[count]) enemy[count] = g.enemy_max[count];
-                if (g.own_has[count]) own[count] = g.own_max[count];
+                if (g.enemy_has[count]) enemy[count] = cf->normalize_grid_by_max_mass ? g.enemy_max[count] / biggest : g.enemy_max[count];
+                if (g.own_has[count]) own[count] = cf->normalize_grid_by_max_mass ? g.own_max[count] / biggest : g.own_max[count];
                 if (cf->virus_enabled && g.vir_has[count]) vir[count] = g.vir_mass[count];
             }
             double lb = py_minS(S, py_max0(midx - gs / 2)), tb = py_minS(S, py_max0(midy - gs / 2));

@@ -395,6 +395,9 @@ def make_params(cfg):
              "USE_LAST_ACTION": cfg.use_last_action, "USE_SECOND_LAST_ACTION": cfg.use_second_last_action}
     for k, v in flags.items():
         setattr(mod, k, bool(v))
+    # the RUN's copy of the flag (the reference's driver rewrites the run folder's networkParameters.py, aigar.py:270-298); the
+    # package-global copy that bot.py:402,439 read stays at its stock value
+    mod.NORMALIZE_GRID_BY_MAX_MASS = bool(cfg.normalize_grid_by_max_mass)
     mod.NUM_OF_GRIDS = sum(bool(getattr(mod, k)) for k in ("PELLET_GRID", "SELF_GRID", "WALL_GRID", "VIRUS_GRID",
                                                            "ENEMY_GRID", "SIZE_GRID", "SELF_GRID_LF", "SELF_GRID_SLF",
                                                            "ENEMY_GRID_LF", "ENEMY_GRID_SLF", "ALL_PLAYER_GRID"))

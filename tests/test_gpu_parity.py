@@ -47,6 +47,10 @@ VARIATIONS = [
     (dict(grid=70, obs_mode=1), None),
     # ALL_PLAYER_GRID (networkParameters.py:88-91)
     (dict(num_nn=2, num_greedy=1, virus=True, split=True, eject=True, overrides={"all_player_grid": 1, "self_grid": 0, "enemy_grid": 0, "self_grid_lf": 0, "enemy_grid_lf": 0}), 32), (dict(overrides={"all_player_grid": 1}), None),
+    # NORMALIZE_GRID_BY_MAX_MASS (the run's flag, bot.py:365,412,422,430)
+    (dict(num_nn=2, num_greedy=1, virus=True, split=True, eject=True, overrides={"normalize_grid_by_max_mass": 1}), 32),
+    (dict(num_nn=1, num_greedy=1, split=True, overrides={"normalize_grid_by_max_mass": 1, "all_player_grid": 1, "self_grid": 0, "enemy_grid": 0,
+                                                         "self_grid_lf": 0, "enemy_grid_lf": 0}), 16),
 ]
 
 

@@ -61,6 +61,10 @@ VARIATIONS = [
     # ALL_PLAYER_GRID (networkParameters.py:88-91): one "biggest cell of any player" channel instead of self / enemy
     dict(num_nn=1, num_greedy=1, virus=True, split=True, eject=True, overrides={"all_player_grid": 1, "self_grid": 0, "enemy_grid": 0, "self_grid_lf": 0, "enemy_grid_lf": 0}),
     dict(overrides={"all_player_grid": 1}),
+    # NORMALIZE_GRID_BY_MAX_MASS in the run's parameters (bot.py:365,412,422,430): cell channels relative to the biggest cell in view
+    dict(num_nn=2, num_greedy=1, virus=True, split=True, eject=True, overrides={"normalize_grid_by_max_mass": 1}),
+    dict(num_nn=1, num_greedy=1, split=True, overrides={"normalize_grid_by_max_mass": 1, "all_player_grid": 1, "self_grid": 0, "enemy_grid": 0,
+                                                        "self_grid_lf": 0, "enemy_grid_lf": 0}),
 ]
 
 
