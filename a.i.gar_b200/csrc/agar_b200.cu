@@ -653,7 +653,7 @@ extern "C" int agar_create(const AgarConfig* cfg, int n_envs, int device, uint64
     int obs_bytes = obs_scratch_bytes(L.grid_squares, e->full != 0);
     /* the pellet index (agar_dev.cuh) lives in the same scratch: it is built after the players have moved (velocities dead)
      * and before the next bot phase (observation tables dead); pools of <= 8 chunks are scanned directly */
-    P.pel_index = e->full && L.pellet_cap > 256 && !(getenv("AGAR_PEL_INDEX") && atoi(getenv("AGAR_PEL_INDEX")) == 0);
+    P.pel_index = e->full && L.pellet_cap > (getenv("AGAR_PEL_INDEX_MIN") ? atoi(getenv("AGAR_PEL_INDEX_MIN")) : 256) && !(getenv("AGAR_PEL_INDEX") && atoi(getenv("AGAR_PEL_INDEX")) == 0);
     const int gb_idx = (P.S + 9) / 10; /* AG_IDX_CELL */
     int idx_bytes = P.pel_index ? ((gb_idx * gb_idx + 3) & ~1) * 2 + L.pellet_cap * 2 + 128 + 64 + 16 : 0; /* counters, entries, sort list, ex-blob list */
     if (idx_bytes > vel_bytes) vel_bytes = idx_bytes;

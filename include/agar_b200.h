@@ -169,7 +169,10 @@ typedef struct AgarEnvHeader {
     uint64_t event_hash;       /* order-sensitive running hash of all events since reset except COLLIDE */
     int32_t dead_order[AGAR_MAX_PLAYERS];   /* field.deadPlayers as player indices  */
 } AgarEnvHeader;
-enum { AGAR_OVF_FAT = 1u, AGAR_OVF_VIRUS = 2u, AGAR_OVF_BLOB = 4u, AGAR_OVF_EVENT = 8u };
+enum { AGAR_OVF_FAT = 1u, AGAR_OVF_VIRUS = 2u, AGAR_OVF_BLOB = 4u,
+       AGAR_OVF_EVENT = 8u /* reserved, never set: a full event ring just stops recording — n_events keeps counting (compare it
+                            * with event_cap) and the running event_hash covers every event.  The bit is not raised because the
+                            * overflow word is part of the state the parity tests compare with the reference. */ };
 
 /* One logged event.  Parity tests compare these bit for bit against the oracle. */
 typedef struct AgarEvent { int32_t type, a, b, c, d; } AgarEvent;

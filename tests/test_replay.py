@@ -124,3 +124,46 @@ def test_replay_fed_by_the_env():
     assert len(rp) == min(total, 4000) and total == 20 * E
     s = rp.sample(np.random.default_rng(0).random(64))
     assert torch.isfinite(s[0]).all() and s[0].shape == (64, b.layout.state_len)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prioritized", [False, True])
+def test_gpu_replay_guards_what_the_reference_raises_on(prioritized):
+    """sampling an empty or one-element buffer (the reference raises: random.randint(0, -1), unbounded recursion in
+    sum(0, len - 1)), indices outside [0, size) and priorities <= 0 (the reference asserts) must neither hang the GPU nor touch
+    memory outside the buffer: the kernels return index 0 / weight 0, leave the trees alone and raise a sticky error flag."""
+    import torch
+    from aigar_b200.replay import GpuReplayBuffer
+    L = 8
+    rp = GpuReplayBuffer(64, L, 2, prioritized, 0.6, 0.4)
+    dev = rp.device
+    u = torch.rand(16, dtype=torch.float64, device=dev)
+    out = rp.sample(u)                      # empty buffer
+    torch.cuda.synchronize()
+    assert rp.error_flags & 1 and int(out[-1].max()) == 0
+    obs = torch.rand((1, L), device=dev)
+    rp.add_batch(obs, torch.rand((1, 2), device=dev), torch.ones(1, device=dev), obs, torch.zeros(1, dtype=torch.uint8, device=dev))
+    out = rp.sample(u)                      # one element: fine for the uniform buffer, too small for the prioritized one
+    torch.cuda.synchronize()
+    assert len(rp) == 1 and int(out[-1].max()) == 0
+    for _ in range(5):
+        rp.add_batch(obs, torch.rand((1, 2), device=dev), torch.ones(1, device=dev), obs, torch.zeros(1, dtype=torch.uint8, device=dev))
+    rp2 = GpuReplayBuffer(64, L, 2, prioritized, 0.6, 0.4)
+    for _ in range(6):
+        rp2.add_batch(obs, torch.rand((1, 2), device=dev), torch.ones(1, device=dev), obs, torch.zeros(1, dtype=torch.uint8, device=dev))
+    assert rp2.error_flags == 0
+    rp2.gather(torch.tensor([0, 5, 6, -1, 1000], dtype=torch.int32, device=dev))   # 6, -1, 1000 are outside [0, 6)
+    torch.cuda.synchronize()
+    assert rp2.error_flags & 2
+    if prioritized:
+        rp3 = GpuReplayBuffer(64, L, 2, True, 0.6, 0.4)
+        for _ in range(6):
+            rp3.add_batch(obs, torch.rand((1, 2), device=dev), torch.ones(1, device=dev), obs, torch.zeros(1, dtype=torch.uint8, device=dev))
+        s0 = rp3.sample(u)
+        rp3.update_priorities(torch.tensor([0, 1, 2], dtype=torch.int32, device=dev), torch.tensor([0.5, 0.0, -1.0], dtype=torch.float64, device=dev))
+        torch.cuda.synchronize()
+        assert rp3.error_flags & 4
+        w = rp3.sample(u)[-2]
+        assert bool(torch.isfinite(w).all())    # the trees were not poisoned by the bad priorities
+        with pytest.raises(Exception):
+            rp3.raise_on_error()
