@@ -458,9 +458,10 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    try:  # one core set per rank: eight ranks polling / launching on one NUMA node otherwise share the same cores
+    try:  # opt-in (AGAR_BENCH_AFFINITY=1): one core set per rank.  Measured on the 8-GPU box (32 vCPUs, one NUMA node): e2e 2.30e9 with
+        # the ranks pinned, 2.40e9 without — the scheduler spreads eight polling threads well enough, so the default is off
         ncpu = os.cpu_count() or 1
-        if world > 1 and ncpu >= 2 * world:
+        if world > 1 and ncpu >= 2 * world and os.environ.get("AGAR_BENCH_AFFINITY", "0") == "1":
             per = ncpu // world
             os.sched_setaffinity(0, set(range(local * per, (local + 1) * per)))
     except Exception:

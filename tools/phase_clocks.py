@@ -27,6 +27,14 @@ for i, n in enumerate(names):
     print("  %-30s mean %8.0f (%4.1f%%)   p95 %8.0f   max %8.0f" % (n, c[:, i].mean(), 100 * c[:, i].mean() / tot.mean(), np.percentile(c[:, i], 95), c[:, i].max()))
 work = c[:, [1, 3, 4, 5, 6, 7, 9, 10, 11, 12]].sum(axis=1)
 print("  work (no waits): mean %.0f  p50 %.0f  p95 %.0f  max %.0f" % (work.mean(), np.median(work), np.percentile(work, 95), work.max()))
-ncells = b.get(lay.GET_NCELLS).cpu().numpy().sum(axis=1) if b.layout.n_agents else None
-if ncells is not None:
-    print("  corr(work, agents' cell count) = %.2f" % np.corrcoef(work, ncells)[0, 1])
+st = b.state_tensor().cpu().numpy()
+L = b.layout
+pl = np.stack([lay.Record(L, st[e].copy()).players["n_cells"].copy() for e in range(min(E, 4096))])
+tot = pl.sum(axis=1)
+w = work[:len(tot)]
+print("  corr(work, live cells of all players) = %.2f" % np.corrcoef(w, tot)[0, 1])
+for lo, hi in ((0, 3), (3, 6), (6, 12), (12, 20), (20, 40), (40, 400)):
+    m = (tot >= lo) & (tot < hi)
+    if m.any():
+        print("  envs with %3d..%3d live cells: %5.1f %% of envs, mean work %8.0f cycles, by phase: %s" % (
+            lo, hi - 1, 100.0 * m.mean(), w[m].mean(), " ".join("%s=%.0f" % (names[i].split()[0], c[:len(tot)][m, i].mean()) for i in (3, 4, 5, 6, 7, 9, 10))))
