@@ -344,13 +344,46 @@ AGAR_HD double agar_cos(double x) {
     return (n & 2) ? -r : r;
 }
 
-/* (cos a, sin a) for a = atan2(dy, dx) — cell.py:49-57: the angle is formed and rounded, then cos and sin are taken of it.
- * (Measured on B200: running sin and cos through one shared code instance in a 2-trip loop shrinks k_simple by 4 % but
- * serialises two chains the scheduler otherwise interleaves: -5 % at 262144 envs.  Keep them as two straight-line calls.) */
+/* sin x and cos x together, the SAME arithmetic as agar_sin / agar_cos.  In every branch of s_sin.c exactly one of the two goes
+ * through the cos-like leaf (do_cos) and the other through the sin-like leaf (Taylor / do_sin), on arguments that differ only in
+ * how the reduction hands them over — so the pair costs ONE evaluation of each leaf, and on a GPU all lanes of a warp run the
+ * cos-like leaf together whatever branch their angle took (calling agar_sin and agar_cos separately runs up to three leaves per
+ * call on different lane subsets). */
+AGAR_HD void agar_sincos(double x, double* sn, double* cs) {
+    const uint32_t k = (uint32_t)(agar_double_to_bits(x) >> 32) & 0x7fffffffu;
+    double ac, dac, as, das;   /* arguments of the cos-like and of the sin-like leaf */
+    int cos_leaf_is_sin;       /* the cos-like leaf's value is sin x (and the sin-like leaf's is cos x) */
+    int neg_s = 0, neg_c = 0, csign = 0;
+    if (k < 0x3feb6000u) {             /* |x| < 0.855469: sin = sin_small(x, 0), cos = do_cos(x, 0) */
+        ac = x, dac = 0.0, as = x, das = 0.0, cos_leaf_is_sin = 0;
+    } else if (k < 0x400368fdu) {      /* |x| < 2.426265: sin = copysign(do_cos(pi/2 - |x|, hp1), x), cos = sin_small(a, da) */
+        const double y = 0x1.921fb54442d18p+0 - fabs(x);
+        ac = y, dac = 0x1.1a62633145c07p-54;
+        as = y + 0x1.1a62633145c07p-54;
+        das = (y - as) + 0x1.1a62633145c07p-54;
+        cos_leaf_is_sin = 1, csign = 1;
+    } else {                            /* reduce_sincos: sin takes quadrant n, cos quadrant n + 1 */
+        double a, da;
+        const int n = agar__reduce_sincos(x, &a, &da);
+        ac = a, dac = da, as = a, das = da;
+        cos_leaf_is_sin = n & 1;        /* n odd: sin x = +-do_cos(a, da), cos x = +-sin_small(a, da) */
+        neg_s = n & 2, neg_c = (n + 1) & 2;
+    }
+    double vc = agar__do_cos(ac, dac);
+    double vs = agar__sin_small(as, das);
+    if (csign) vc = agar_copysign(vc, x);
+    double s_val = cos_leaf_is_sin ? vc : vs, c_val = cos_leaf_is_sin ? vs : vc;
+    if (neg_s) s_val = -s_val;
+    if (neg_c) c_val = -c_val;
+    if (k < 0x3e500000u) s_val = x;   /* |x| < 2^-26 */
+    if (k < 0x3e400000u) c_val = 1.0; /* |x| < 2^-27 */
+    *sn = s_val, *cs = c_val;
+}
+
+/* (cos a, sin a) for a = atan2(dy, dx) — cell.py:49-57: the angle is formed and rounded, then cos and sin are taken of it. */
 AGAR_HD void agar_dir(double dy, double dx, double* c, double* s) {
     const double a = agar_atan2(dy, dx);
-    *c = agar_cos(a);
-    *s = agar_sin(a);
+    agar_sincos(a, s, c);
 }
 
 /* Python's round(x, nd) for |x| * 10^nd < 2^51 (bot.py:16-20,449): the multiple of 10^-nd nearest to the

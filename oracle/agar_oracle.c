@@ -1485,6 +1485,10 @@ uint64_t oracle_pm_trig_mismatches(uint64_t n, uint64_t seed) {
         double s1 = agar_sin(ang), s2 = sin(ang), c1 = agar_cos(ang), c2 = cos(ang);
         bad += memcmp(&s1, &s2, 8) != 0;
         bad += memcmp(&c1, &c2, 8) != 0;
+        double s3, c3;
+        agar_sincos(ang, &s3, &c3); /* the paired form the kernels call */
+        bad += memcmp(&s3, &s2, 8) != 0;
+        bad += memcmp(&c3, &c2, 8) != 0;
     }
 #undef U01
     for (int yy = -300; yy <= 300; ++yy) /* fresh cells and pellets sit on integer coordinates */
