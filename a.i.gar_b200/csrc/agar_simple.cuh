@@ -319,7 +319,12 @@ DEV void s_field_update(SReg& r, const SPtr& q, const DevParams& P, uint32_t env
     r.flags |= AGAR_CF_INHASH;
     /* playerPelletOverlap (field.py:207-213): slot order, the cell grows as it eats.
      * Phase 1: integer window |d| <= radius + 2 around the cell -> candidate bitmask over this lane's slots. */
-    const Rect rc = rect_of(P.S, r.x, r.y, radius); /* candidate rectangle: fixed before the cell grows */
+    /* The candidate rectangle is fixed before the cell grows (field.py:207).  While the cell has not grown this frame the
+     * rectangle test is implied by the eat test — overlap with the cell as the bigger one puts the pellet's integer centre
+     * strictly inside (x - r, x + r), i.e. inside the coordinates [bucket_left, limit - 1] the cell's buckets cover
+     * (axis_range), and the pellet's own bucket px / 20 is one of its rectangle's — so it is only evaluated, from the
+     * pre-growth radius, for pellets met after the first one eaten in the frame. */
+    const double radius0 = radius;
     const double cx = r.x, cy = r.y;
     const int icx = (int)cx, icy = (int)cy;
     const int cap = P.L.pellet_cap;
@@ -364,8 +369,8 @@ DEV void s_field_update(SReg& r, const SPtr& q, const DevParams& P, uint32_t env
         s_sync<W>(); /* every lane has read its tile's candidate before lane sub == 0 may clear the slot */
         if (first != S_NONE) {
             int px = AGAR_PELLET_X(pk), py = AGAR_PELLET_Y(pk), pm = AGAR_PELLET_M(pk);
-            if (rect_hit(rc, pellet_rect(px, py)) &&
-                overlap(cx, cy, mass, radius, (double)px, (double)py, (double)pm, P.pellet_r[pm & 3]) && mass > 1.25 * (double)pm) {
+            if (overlap(cx, cy, mass, radius, (double)px, (double)py, (double)pm, P.pellet_r[pm & 3]) && mass > 1.25 * (double)pm &&
+                (n_eaten == 0 || rect_hit(rect_of(P.S, cx, cy, radius0), pellet_rect(px, py)))) {
                 s_log(r, q, P, sub == 0, AGAR_EV_EAT_PELLET, 0, (int)r.uid, first, 0);
                 double nm = mass + (double)pm;
                 if (!(nm < AG_MAX_MASS)) nm = AG_MAX_MASS;

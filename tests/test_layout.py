@@ -57,6 +57,36 @@ def test_pellet_rectangle_closed_form():
                 assert (b0.value, b1.value) == ((x - 1 if x > 0 else 0) // 20, x // 20), (S, m, x)
 
 
+def test_eat_test_implies_shared_bucket():
+    """k_simple skips the hash-rectangle test for the first pellet a cell eats in a frame: whenever the eat test passes
+    (cell.py:143-152 overlap with the cell as the bigger one) the pellet's rectangle meets the cell's (pre-growth) one."""
+    lib = orc.load()
+    rng = np.random.default_rng(5)
+    a0, a1, c0, c1 = (ctypes.c_int() for _ in range(4))
+    checked = 0
+    for S in (75, 106, 300):
+        for _ in range(6000):
+            mass = float(rng.uniform(4, 400))
+            r = float(np.sqrt(mass / np.pi))
+            x, y = rng.uniform(0, S, 2)
+            if rng.random() < 0.3:  # hug a wall or a bucket edge
+                x = float(rng.choice([0.0, S, 20.0 * rng.integers(0, S // 20 + 1)])) + rng.uniform(-1e-9, 1e-9)
+                x = min(max(x, 0.0), float(S))
+            for _ in range(8):
+                ang, d = rng.uniform(0, 2 * np.pi), r / np.sqrt(1.1) * rng.choice([rng.uniform(0, 1), rng.uniform(0.999, 1.001)])
+                px, py = int(round(x + d * np.cos(ang))), int(round(y + d * np.sin(ang)))
+                if not (0 <= px < S and 0 <= py < S):
+                    continue
+                d2 = (x - px) * (x - px) + (y - py) * (y - py)
+                if not d2 * 1.1 < r * r:
+                    continue
+                checked += 1
+                lib.oracle_axis_range(float(x), r, S, ctypes.byref(a0), ctypes.byref(a1))
+                lib.oracle_axis_range(float(y), r, S, ctypes.byref(c0), ctypes.byref(c1))
+                assert a0.value <= px // 20 <= a1.value and c0.value <= py // 20 <= c1.value, (S, mass, x, y, px, py)
+    assert checked > 20000
+
+
 def test_sharding_partition():
     from aigar_b200.sharding import shard_envs
     for total in (1, 7, 4096, 65536 + 3):
