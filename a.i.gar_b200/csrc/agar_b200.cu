@@ -219,6 +219,7 @@ k_main(const __grid_constant__ DevParams P, uint8_t* __restrict__ state, const f
 struct SimplePlan {
     int frame_sync; /* CTA barrier at every frame: the warps of a CTA fetch the same instructions together */
     int strideB; /* bytes between the staged [pellets .. end of record] regions of consecutive envs */
+    int grid_off; /* byte offset of the env's G x G observation accumulator inside its region; 0: accumulate in the caller's row */
 };
 /* one lane per env is throughput-bound: cap registers at 128 for 8 CTAs / SM (measured +10..50 % at >= 64k envs);
  * wider tiles are latency-bound at small env counts and prefer the uncapped allocation (measured) */
@@ -253,6 +254,7 @@ k_simple(const __grid_constant__ DevParams P, const SimplePlan SP, uint8_t* __re
     q.c = (AgarCell*)(rec + P.L.off_cells);
     q.pel = (uint32_t*)b;
     q.ev = (AgarEvent*)(b + (P.L.off_events - P.L.off_pellets));
+    q.grid = SP.grid_off ? (uint32_t*)(b + SP.grid_off) : nullptr;
     SReg r;
     s_load(r, q);
     float* row = (obs != nullptr && valid) ? obs + (size_t)env * P.L.state_len : nullptr;
@@ -596,6 +598,16 @@ extern "C" int agar_set_tile_width(AgarEnv* e, int W) {
         !getenv("AGAR_GENERAL_KERNEL")) {
         int tail_words = (int)((e->L.record_bytes - e->L.off_pellets) / 4);
         e->sp.strideB = (tail_words | 1) * 4;
+        e->sp.grid_off = 0;
+        /* the observation's G x G sums are accumulated in shared memory and leave once, as consecutive floats of the row
+         * (measured: 4096 envs W=8 +1.2 %, 65536 envs W=2 +8 %).  Not at one lane per env: 484 more bytes per env halve the
+         * resident envs per SM there (1M envs: 3.28e9 -> 1.52e9), and a lone lane's stores are strided either way. */
+        const char* genv = getenv("AGAR_SIMPLE_OBS_SMEM");
+        if (genv ? atoi(genv) != 0 : W >= 2) {
+            const int gg = e->L.grid_squares * e->L.grid_squares;
+            e->sp.grid_off = tail_words * 4;
+            e->sp.strideB = ((tail_words + gg) | 1) * 4;
+        }
         if (e->L.pellet_cap > 128 * W) return fail(e, AGAR_E_UNSUPPORTED, "pellet pool too large for this tile width%s", "");
         int threads = 128; /* measured (round 2, exact libm arithmetic): four warps per CTA beat two at every batch size (4096 envs: 7.7e8 vs 7.0e8) */
         const char* tenv = getenv("AGAR_SIMPLE_THREADS");

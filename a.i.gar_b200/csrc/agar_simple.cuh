@@ -49,6 +49,7 @@ struct SPtr {
     AgarCell* c;
     uint32_t* pel;    /* shared memory: pellet slots */
     AgarEvent* ev;    /* shared memory: event ring   */
+    uint32_t* grid;   /* shared memory: G x G mass sums of the observation being built (nullptr: accumulate in the caller's row) */
 };
 
 DEV void s_load(SReg& r, const SPtr& q) {
@@ -203,8 +204,12 @@ DEV void s_observe(SReg& r, const SPtr& q, const DevParams& P, bool mine, float*
     }
     const bool out = mine && row != nullptr;
     if (!s_any<W>(out)) return;
+    const bool staged = q.grid != nullptr;
     if (out) { /* clear the row; extras: [fov size], [total mass] (bot.py:302-323) */
-        for (int i = sub; i < GG; i += W) row[i] = 0.f;
+        if (staged)
+            for (int i = sub; i < GG; i += W) q.grid[i] = 0u;
+        else
+            for (int i = sub; i < GG; i += W) row[i] = 0.f;
         if (sub == 0) {
             int n = GG;
             if (P.cfg.use_fovsize) row[n++] = (float)r.fov_size;
@@ -286,13 +291,23 @@ DEV void s_observe(SReg& r, const SPtr& q, const DevParams& P, bool mine, float*
                 int sr = sheared ? cc + rr : cc, sc = rr;
                 if (sr >= G) sr -= G, sc += 1;
                 int id = sr + sc * G;
-                if (ok && cc >= 0 && rr >= 0 && sc < G && !((row_bad >> sc & 1) || (col_bad >> sr & 1))) atomicAdd(&row[id], fm);
+                if (ok && cc >= 0 && rr >= 0 && sc < G && !((row_bad >> sc & 1) || (col_bad >> sr & 1))) {
+                    if (staged)
+                        atomicAdd(&q.grid[id], (unsigned)pm); /* pellet masses are small integers: the float sum is this integer, in any order */
+                    else
+                        atomicAdd(&row[id], fm);
+                }
             };
             put(c0, r0);
             put(c1, r0);
             put(c0, r1);
             put(c1, r1);
         }
+    }
+    if (staged) { /* the finished grid leaves shared memory once, as consecutive floats of the env's row */
+        s_sync<W>();
+        if (out)
+            for (int i = sub; i < GG; i += W) row[i] = (float)q.grid[i];
     }
 }
 
