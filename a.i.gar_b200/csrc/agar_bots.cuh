@@ -469,6 +469,95 @@ DEV void set_command_point(Ctx<W>& c, const DevParams& P, int k, double a0, doub
     p->do_eject = eject;
 }
 
+/* cooperative; Bot.getSimpleStateRepresentation (bot.py:511-548; GRID_VIEW_ENABLED = False, networkParameters.py:119): first own cell,
+ * closest enemy cell in the field of view, closest pellet in the INTEGER field of view (relative positions / radii rounded to 5
+ * decimals), distances to the visible field edges.  `min(..., key=squaredDistance)` keeps the first minimal candidate of the list:
+ * every lane keeps its own first minimum over a strided share, the tile reduces (distance, canonical position) lexicographically. */
+template <int W>
+DEV void simple_closest_reduce(Ctx<W>& c, double& d, int& ord) {
+    for (int off = W / 2; off > 0; off >>= 1) {
+        const double od = c.t.shfl_xor(d, off);
+        const int oo = c.t.shfl_xor(ord, off);
+        if (oo >= 0 && (ord < 0 || od < d || (od == d && oo < ord))) d = od, ord = oo;
+    }
+}
+template <int W>
+DEV void simple_state_agent(Ctx<W>& c, const DevParams& P, int k, float* obs) {
+    AgarPlayer* p = &c.pl[k];
+    if (c.lane == 0 && !c.fov_done) update_fov(c, P, k);
+    c.t.sync();
+    if (obs == nullptr) return; /* a decision inside a multi-frame step: only the field-of-view caches advance */
+    const double fov = p->fov_size, fx = p->fov_x, fy = p->fov_y;
+    const int x = (int)fx, y = (int)fy;
+    const int left = x - (int)(fov / 2), top = y - (int)(fov / 2), size = (int)fov;
+    const AgarCell* first = CELLP(c, P, k, 0);
+    const double ox = first->x, oy = first->y;
+    const int K = P.L.n_players, cap = P.L.cell_cap;
+    /* closest enemy cell, field.py:434-436 through the player table (rectangle + INHASH) */
+    double ed = 0.0;
+    int eo = -1;
+    {
+        const Rect ra = rect_of(P.S, fx, fy, fov / 2);
+        for (int idx = c.lane; idx < K * cap; idx += W) {
+            const int k2 = idx / cap, j = idx - k2 * cap;
+            if (k2 == k || j >= c.pl[k2].n_cells) continue;
+            const AgarCell* o = CELLP(c, P, k2, j);
+            if (!(o->flags & AGAR_CF_INHASH) || !rect_hit(ra, rect_of(P.S, o->x, o->y, o->radius)) || !in_fov(o->x, o->y, o->radius, fx, fy, fov))
+                continue;
+            const double d = (o->x - ox) * (o->x - ox) + (o->y - oy) * (o->y - oy); /* cell.py:158-160 */
+            if (eo < 0 || d < ed) ed = d, eo = idx;
+        }
+        simple_closest_reduce<W>(c, ed, eo);
+    }
+    /* closest pellet, getPelletsInFov(midPoint, int(size)) field.py:442-444: integer pellets by slot, then the ex-blob pellets */
+    double pd = 0.0;
+    int po = -1;
+    {
+        const double isz = (double)size;
+        const Rect ra = rect_of(P.S, fx, fy, isz / 2);
+        for (int s = c.lane; s < P.L.pellet_cap; s += W) {
+            const uint32_t pk = c.pel[s];
+            if (!pk) continue;
+            const int px = AGAR_PELLET_X(pk), py = AGAR_PELLET_Y(pk), pm = AGAR_PELLET_M(pk);
+            if (!rect_hit(ra, pellet_rect(px, py)) || !in_fov((double)px, (double)py, P.pellet_r[pm & 3], fx, fy, isz)) continue;
+            const double d = ((double)px - ox) * ((double)px - ox) + ((double)py - oy) * ((double)py - oy);
+            if (po < 0 || d < pd) pd = d, po = s;
+        }
+        for (int s = c.lane; s < P.L.fat_cap; s += W) {
+            const AgarFatPellet* f = &c.fat[s];
+            if (f->mass == 0) continue;
+            if (!rect_hit(ra, rect_of(P.S, f->x, f->y, f->radius)) || !in_fov(f->x, f->y, f->radius, fx, fy, isz)) continue;
+            const double d = (f->x - ox) * (f->x - ox) + (f->y - oy) * (f->y - oy);
+            if (po < 0 || d < pd) pd = d, po = P.L.pellet_cap + s; /* a lane meets its integer pellets first: ascending canonical position */
+        }
+        simple_closest_reduce<W>(c, pd, po);
+    }
+    if (c.lane == 0) {
+        const double dsz = (double)size, S = (double)P.S;
+        auto rel = [&](double v, int base) { return (float)agar_round_dec((v - base) / dsz, 1e5); }; /* getRelativeCellPos :16-20 */
+        auto rad = [&](double r) { return (float)agar_round_dec(r <= dsz ? r / dsz : 1.0, 1e5); };  /* isRelativeCellData :635-637 */
+        obs[0] = rel(ox, left), obs[1] = rel(oy, top), obs[2] = rad(first->radius);
+        if (eo >= 0) {
+            const AgarCell* o = c.cells + eo;
+            obs[3] = rel(o->x, left), obs[4] = rel(o->y, top), obs[5] = rad(o->radius);
+        } else
+            obs[3] = obs[4] = obs[5] = 0.f;
+        if (po >= P.L.pellet_cap) {
+            const AgarFatPellet* f = &c.fat[po - P.L.pellet_cap];
+            obs[6] = rel(f->x, left), obs[7] = rel(f->y, top);
+        } else if (po >= 0) {
+            const uint32_t pk = c.pel[po];
+            obs[6] = rel((double)AGAR_PELLET_X(pk), left), obs[7] = rel((double)AGAR_PELLET_Y(pk), top);
+        } else
+            obs[6] = obs[7] = 0.f;
+        obs[8] = left <= 0 ? (float)((double)x / dsz) : 1.f; /* :541-547 */
+        obs[9] = left + size >= P.S ? (float)((S - x) / dsz) : 1.f;
+        obs[10] = top <= 0 ? (float)((double)y / dsz) : 1.f;
+        obs[11] = top + size >= P.S ? (float)((S - y) / dsz) : 1.f;
+    }
+    c.t.sync();
+}
+
 /* cooperative; first half of move_NN (bot.py:195-217) + makeMove :253 */
 template <int W, bool FULL>
 DEV void nn_turn_begin(Ctx<W>& c, const DevParams& P, int k, float* obs) {
@@ -503,7 +592,12 @@ DEV void nn_turn_begin(Ctx<W>& c, const DevParams& P, int k, float* obs) {
     }
     do_obs = c.t.shfl(do_obs, 0);
     CLK_IN(c, 9); /* reward / frame-skip bookkeeping */
-    if (do_obs) observe_agent<W, FULL>(c, P, k, k, obs);
+    if (do_obs) {
+        if (FULL && P.cfg.simple_state)
+            simple_state_agent<W>(c, P, k, obs);
+        else
+            observe_agent<W, FULL>(c, P, k, k, obs);
+    }
     CLK_IN(c, 10); /* observation */
 }
 /* lane 0; second half of move_NN (bot.py:223-232) + tail of makeMove (:256-270) */

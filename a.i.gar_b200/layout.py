@@ -14,6 +14,7 @@ ACTION_DIM = 4
 
 BOT_NN, BOT_GREEDY, BOT_RANDOM = 0, 1, 2
 OBS_REFERENCE, OBS_CANONICAL = 0, 1
+SIMPLE_STATE_LEN = 12  # Bot.getSimpleStateRepresentation, bot.py:511-548 (AGAR_SIMPLE_STATE_LEN)
 CF_EJECT, CF_INHASH = 1, 2
 
 (GET_REWARD, GET_DONE, GET_VALID, GET_NEED_ACTION, GET_MASS, GET_FOV, GET_NCELLS, GET_ALIVE, GET_STATS,
@@ -43,7 +44,8 @@ class AgarConfig(ctypes.Structure):
         ("fat_cap", ctypes.c_int32), ("virus_cap", ctypes.c_int32), ("blob_cap", ctypes.c_int32),
         ("event_cap", ctypes.c_int32),
         ("pellet_cap", ctypes.c_int32), ("all_player_grid", ctypes.c_int32), ("normalize_grid_by_max_mass", ctypes.c_int32),
-        ("reserved", ctypes.c_int32 * 4),
+        ("simple_state", ctypes.c_int32),
+        ("reserved", ctypes.c_int32 * 3),
         ("reward_scale", ctypes.c_double), ("reward_term", ctypes.c_double),
         ("death_term", ctypes.c_double), ("death_factor", ctypes.c_double),
     ]
@@ -97,7 +99,7 @@ assert EVENT_DT.itemsize == 20
 
 def derive_config(num_nn=1, num_greedy=0, num_random=0, virus=False, split=False, eject=False, grid=11,
                   frame_skip=7, obs_mode=OBS_REFERENCE, event_cap=0, pellet_spawn=True, reward_scale=2.0,
-                  reward_term=0.0, death_term=-40.0, death_factor=1.5, mass_as_reward=False, overrides=None):
+                  reward_term=0.0, death_term=-40.0, death_factor=1.5, mass_as_reward=False, grid_view=True, overrides=None):
     """Build an AgarConfig the way src/model/networkParameters.py:75-102 derives its flags."""
     c = AgarConfig()
     k = num_nn + num_greedy + num_random
@@ -129,6 +131,7 @@ def derive_config(num_nn=1, num_greedy=0, num_random=0, virus=False, split=False
     c.use_second_last_action = 0
     c.mass_as_reward = int(mass_as_reward)
     c.obs_mode = obs_mode
+    c.simple_state = int(not grid_view)  # GRID_VIEW_ENABLED, networkParameters.py:119
     c.event_cap = event_cap
     c.reward_scale = reward_scale
     c.reward_term = reward_term
@@ -177,8 +180,10 @@ def layout_for_config(c):
     L.n_extra = (int(bool(c.use_fovsize)) + int(bool(c.use_totalmass)) + 4 * int(bool(c.use_last_action)) +
                  4 * int(bool(c.use_second_last_action)) + int(bool(c.use_last_fovsize)))
     L.state_len = g * g * L.n_grids + L.n_extra
+    if c.simple_state:
+        L.n_grids, L.n_extra, L.state_len = 0, 0, SIMPLE_STATE_LEN
     L.action_len = 2 + int(bool(c.enable_split)) + int(bool(c.enable_eject))
-    L.n_hist = 4 if (c.self_grid_lf or c.self_grid_slf or c.enemy_grid_lf or c.enemy_grid_slf) else 0
+    L.n_hist = 4 if (not c.simple_state and (c.self_grid_lf or c.self_grid_slf or c.enemy_grid_lf or c.enemy_grid_slf)) else 0
     off = 0
     L.off_header = off
     off = _align(off + HEADER_DT.itemsize, 16)

@@ -47,6 +47,8 @@ enum { AGAR_BOT_NN = 0, AGAR_BOT_GREEDY = 1, AGAR_BOT_RANDOM = 2 };
 /* grid-vision binning: reproduce src/model/spatialHashTable.py:19,91-112 operation by operation
  * (including the ceil()/int() rounding artefacts), or the canonical G-column binning */
 enum { AGAR_OBS_REFERENCE = 0, AGAR_OBS_CANONICAL = 1 };
+/* length of Bot.getSimpleStateRepresentation: 3 (own cell) + 3 (closest enemy) + 2 (closest pellet) + 4 (field edges) */
+#define AGAR_SIMPLE_STATE_LEN 12
 
 /* ------------------------------------------------------------------ config */
 /* Mirrors the flag subset of src/model/networkParameters.py that the env path reads
@@ -78,7 +80,11 @@ typedef struct AgarConfig {
                                            * 422,430): the own / enemy / all-player channels are divided by the mass of the biggest
                                            * player cell in view.  (bot.py:402,439 — pellet and virus channels — read the package-
                                            * global flag instead, which the reference's driver never rewrites: not modelled.)      */
-    int32_t reserved[4];
+    int32_t simple_state;                 /* GRID_VIEW_ENABLED = False (networkParameters.py:119): observations are the 12 values of
+                                           * Bot.getSimpleStateRepresentation (bot.py:511-548) — first own cell, closest enemy cell,
+                                           * closest pellet (relative to the integer field of view), distances to the visible field
+                                           * edges — instead of the grids; state_len = 12, the channel / extra flags are ignored */
+    int32_t reserved[3];
     double reward_scale;                  /* REWARD_SCALE :70 */
     double reward_term;                   /* REWARD_TERM  :69 */
     double death_term;                    /* DEATH_TERM   :71 */

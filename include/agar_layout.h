@@ -67,9 +67,10 @@ static inline int agar_layout_compute(const AgarConfig* c, AgarLayout* L) {
     L->n_extra = (c->use_fovsize != 0) + (c->use_totalmass != 0) + 4 * (c->use_last_action != 0) +
                  4 * (c->use_second_last_action != 0) + (c->use_last_fovsize != 0);
     L->state_len = c->grid_squares * c->grid_squares * L->n_grids + L->n_extra;
+    if (c->simple_state) L->n_grids = 0, L->n_extra = 0, L->state_len = AGAR_SIMPLE_STATE_LEN; /* bot.py:511-548 */
     L->action_len = 2 + (c->enable_split != 0) + (c->enable_eject != 0);
     /* history grids (bot.py:479-495) only exist when a last-frame channel is enabled */
-    L->n_hist = (c->self_grid_lf || c->self_grid_slf || c->enemy_grid_lf || c->enemy_grid_slf) ? 4 : 0;
+    L->n_hist = (!c->simple_state && (c->self_grid_lf || c->self_grid_slf || c->enemy_grid_lf || c->enemy_grid_slf)) ? 4 : 0;
     uint64_t off = 0;
     L->off_header = off;
     off = agar__align(off + sizeof(AgarEnvHeader), 16);

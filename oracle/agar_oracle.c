@@ -1042,6 +1042,84 @@ static void observe_agent(OracleEnv* e, int k, int agent, float* obs, double* ob
         for (int i = 0; i < n; ++i) obs64[i] = out[i];
 }
 
+/* Bot.getSimpleStateRepresentation (bot.py:511-548; GRID_VIEW_ENABLED = False, networkParameters.py:119): 12 values.
+ * Candidates come from the hash tables like everywhere else (rectangle + INHASH flag); `min(..., key=squaredDistance)` keeps the
+ * FIRST minimal candidate of the list, which the harness orders canonically (int pellets by slot, then ex-blob pellets; players
+ * by index, cells by list position) — the reference's own order is a Python set's. */
+static void rel_cell_pos(double cx, double cy, int left, int top, int size, double* o) { /* getRelativeCellPos :16-20 */
+    o[0] = round_dec((cx - left) / size, 5);
+    o[1] = round_dec((cy - top) / size, 5);
+}
+static void simple_state_agent(OracleEnv* e, int k, float* obs, double* obs64) {
+    AgarPlayer* p = &e->pl[k];
+    double S = (double)e->S;
+    update_fov_size(e, k);
+    update_fov_pos(e, k);
+    const double fov = p->fov_size, fx = p->fov_x, fy = p->fov_y;
+    const int x = (int)fx, y = (int)fy;
+    const int left = x - (int)(fov / 2), top = y - (int)(fov / 2), size = (int)fov;
+    const AgarCell* first = CELLP(e, k, 0);
+    double out[AGAR_SIMPLE_STATE_LEN];
+    memset(out, 0, sizeof(out));
+    /* getCellDataOwnPlayer :648-652 -> isRelativeCellData :635-637 of the first cell */
+    rel_cell_pos(first->x, first->y, left, top, size, out);
+    out[2] = round_dec(first->radius <= size ? first->radius / size : 1.0, 5);
+    /* closest enemy cell in the (float) field of view: field.py:434-436 */
+    {
+        Rect ra = rect_of(e, fx, fy, fov / 2);
+        const AgarCell* best = NULL;
+        double bd = 0;
+        for (int k2 = 0; k2 < e->L.n_players; ++k2) {
+            if (k2 == k) continue;
+            for (int j = 0; j < e->pl[k2].n_cells; ++j) {
+                const AgarCell* o = CELLP(e, k2, j);
+                if (!(o->flags & AGAR_CF_INHASH) || !rect_hit(ra, rect_of(e, o->x, o->y, o->radius)) ||
+                    !in_fov(o->x, o->y, o->radius, fx, fy, fov))
+                    continue;
+                double d = (o->x - first->x) * (o->x - first->x) + (o->y - first->y) * (o->y - first->y); /* cell.py:158-160 */
+                if (!best || d < bd) best = o, bd = d;
+            }
+        }
+        if (best) {
+            rel_cell_pos(best->x, best->y, left, top, size, out + 3);
+            out[5] = round_dec(best->radius <= size ? best->radius / size : 1.0, 5);
+        }
+    }
+    /* closest pellet in the INTEGER field of view: getPelletsInFov(midPoint, int(size)), field.py:442-444 */
+    {
+        const double isz = (double)size;
+        Rect ra = rect_of(e, fx, fy, isz / 2);
+        int have = 0;
+        double bd = 0, bx = 0, by = 0;
+        for (int s = 0; s < e->L.pellet_cap; ++s) {
+            uint32_t pk = e->pel[s];
+            if (!pk) continue;
+            int px = AGAR_PELLET_X(pk), py = AGAR_PELLET_Y(pk), pm = AGAR_PELLET_M(pk);
+            double pr = pellet_radius(pm);
+            if (!rect_hit(ra, rect_of(e, px, py, pr)) || !in_fov(px, py, pr, fx, fy, isz)) continue;
+            double d = (px - first->x) * (px - first->x) + (py - first->y) * (py - first->y);
+            if (!have || d < bd) have = 1, bd = d, bx = px, by = py;
+        }
+        for (int s = 0; s < e->L.fat_cap; ++s) {
+            const AgarFatPellet* f = &e->fat[s];
+            if (f->mass == 0) continue;
+            if (!rect_hit(ra, rect_of(e, f->x, f->y, f->radius)) || !in_fov(f->x, f->y, f->radius, fx, fy, isz)) continue;
+            double d = (f->x - first->x) * (f->x - first->x) + (f->y - first->y) * (f->y - first->y);
+            if (!have || d < bd) have = 1, bd = d, bx = f->x, by = f->y;
+        }
+        if (have) rel_cell_pos(bx, by, left, top, size, out + 6);
+    }
+    /* distances to the visible field edges :541-547 (ints divided by an int: true division) */
+    out[8] = left <= 0 ? (double)x / size : 1.0;
+    out[9] = left + size >= e->S ? (S - x) / size : 1.0;
+    out[10] = top <= 0 ? (double)y / size : 1.0;
+    out[11] = top + size >= e->S ? (S - y) / size : 1.0;
+    if (obs)
+        for (int i = 0; i < AGAR_SIMPLE_STATE_LEN; ++i) obs[i] = (float)out[i];
+    if (obs64)
+        for (int i = 0; i < AGAR_SIMPLE_STATE_LEN; ++i) obs64[i] = out[i];
+}
+
 /* ------------------------------------------------------------------ bots (bot.py) */
 static double bot_reward(OracleEnv* e, int k) { /* getReward :654-667 */
     const AgarConfig* cf = &e->cfg;
@@ -1094,7 +1172,12 @@ static void nn_turn_begin(OracleEnv* e, int k, int agent, float* obs, double* ob
         }
     }
     if (!B->skipping) {
-        if (p->alive) observe_agent(e, k, agent, obs, obs64);
+        if (p->alive) {
+            if (e->cfg.simple_state)
+                simple_state_agent(e, k, obs, obs64);
+            else
+                observe_agent(e, k, agent, obs, obs64);
+        }
         if (B->has_old_state) {
             B->time += 1;
             B->exp_valid = 1;

@@ -404,6 +404,11 @@ def make_params(cfg):
     mod.EXTRA_INPUT = (bool(mod.USE_FOVSIZE) + bool(mod.USE_TOTALMASS) + bool(mod.USE_LAST_ACTION) * 4 +
                        bool(mod.USE_SECOND_LAST_ACTION) * 4 + bool(mod.USE_LAST_FOVSIZE))
     mod.STATE_REPR_LEN = mod.GRID_SQUARES_PER_FOV ** 2 * mod.NUM_OF_GRIDS + mod.EXTRA_INPUT
+    if cfg.simple_state:  # GRID_VIEW_ENABLED = False: Bot.getSimpleStateRepresentation (12 values).  The reference leaves STATE_REPR_LEN
+        # at the grid formula (networkParameters.py:102 does not look at the flag), which is why none of its learners can consume
+        # this representation; the record layouts here carry the true length
+        mod.GRID_VIEW_ENABLED = False
+        mod.STATE_REPR_LEN = lay.SIMPLE_STATE_LEN
     mod.GATHER_EXP = True
     return mod
 

@@ -65,6 +65,10 @@ VARIATIONS = [
     dict(num_nn=2, num_greedy=1, virus=True, split=True, eject=True, overrides={"normalize_grid_by_max_mass": 1}),
     dict(num_nn=1, num_greedy=1, split=True, overrides={"normalize_grid_by_max_mass": 1, "all_player_grid": 1, "self_grid": 0, "enemy_grid": 0,
                                                         "self_grid_lf": 0, "enemy_grid_lf": 0}),
+    # GRID_VIEW_ENABLED = False (networkParameters.py:119): Bot.getSimpleStateRepresentation, bot.py:511-548
+    dict(grid_view=False),
+    dict(num_nn=1, num_greedy=1, virus=True, split=True, eject=True, grid_view=False),
+    dict(num_nn=2, num_greedy=3, split=True, eject=True, grid_view=False, frame_skip=2),
 ]
 
 

@@ -28,6 +28,9 @@ CASES = {
     "all_player_1v1_canonical": (dict(num_nn=1, num_greedy=1, virus=True, split=True, eject=True, obs_mode=1,
                                       overrides={"all_player_grid": 1, "self_grid": 0, "enemy_grid": 0, "self_grid_lf": 0,
                                                  "enemy_grid_lf": 0}), 320, 17, 3, 80),
+    # GRID_VIEW_ENABLED = False: Bot.getSimpleStateRepresentation (bot.py:511-548), 12 values per observation
+    "simple_state_1v1": (dict(num_nn=1, num_greedy=1, virus=True, split=True, eject=True, grid_view=False), 480, 19, 1, 80),
+    "simple_state_arena": (dict(num_nn=3, num_greedy=5, virus=True, split=True, eject=True, grid_view=False, frame_skip=3), 160, 23, 2, 40),
 }
 
 
