@@ -297,14 +297,26 @@ DEV void observe_agent(Ctx<W>& c, const DevParams& P, int k, int agent, float* o
     } else {
         for (int i = c.lane; i < nbk; i += W) sc.tab[i] = (double)sc.pel_i[i];
         c.t.sync();
-        if (c.lane == 0 && c.h->n_fat) /* float pellets are added after the integer ones, in slot order (canonical candidate order) */
-            for (int s = 0; s < P.L.fat_cap; ++s) {
-                const AgarFatPellet* f = &c.fat[s];
-                if (f->mass == 0) continue;
-                if (!rect_hit(ra, rect_of(P.S, f->x, f->y, f->radius)) || !in_fov(f->x, f->y, f->radius, fx, fy, fov)) continue;
-                double fm = f->mass;
-                for_each_fov_bucket(f->x, f->y, f->radius, left, top, fov, gs, inv, cols, canon,
-                                    [&](int id) { sc.tab[id] = sc.tab[id] + fm; });
+        /* float pellets are added after the integer ones, in slot order (canonical candidate order; the float64 sums depend on
+         * it).  The slots are tested W at a time — one memory latency per round instead of one per slot on a lone lane — and
+         * only the few that are in view add their mass, one after the other in ascending slot order. */
+        if (c.h->n_fat)
+            for (int base = 0; base < P.L.fat_cap; base += W) {
+                const int sl = base + c.lane;
+                AgarFatPellet f = {};
+                if (sl < P.L.fat_cap) f = c.fat[sl];
+                const bool hit = f.mass != 0 && rect_hit(ra, rect_of(P.S, f.x, f.y, f.radius)) && in_fov(f.x, f.y, f.radius, fx, fy, fov);
+                unsigned hits = c.t.ballot(hit);
+                while (hits) {
+                    const int b = __ffs((int)hits) - 1;
+                    hits &= hits - 1;
+                    if (c.lane == b) {
+                        const double fm = f.mass;
+                        for_each_fov_bucket(f.x, f.y, f.radius, left, top, fov, gs, inv, cols, canon,
+                                            [&](int id) { sc.tab[id] = sc.tab[id] + fm; });
+                    }
+                    c.t.sync();
+                }
             }
         c.t.sync();
         for (int idx = c.lane; idx < GG; idx += W) {
@@ -666,12 +678,20 @@ DEV void scripted_turn(Ctx<W>& c, const DevParams& P, int k) {
             consider((double)px, (double)py, (double)pm, ord0 + s);
         });
         ord0 += P.L.pellet_cap;
-        for (int s = c.lane; s < P.L.fat_cap; s += W) {
-            const AgarFatPellet* f = &c.fat[s];
-            if (f->mass == 0) continue;
-            if (!rect_hit(ra, rect_of(P.S, f->x, f->y, f->radius)) || !in_fov(f->x, f->y, f->radius, fx, fy, fov)) continue;
-            consider(f->x, f->y, f->mass, ord0 + s);
-        }
+        if (c.h->n_fat) /* mostly free slots: four independent mass loads in flight per lane, then the rare live ones */
+            for (int base = c.lane; base < P.L.fat_cap; base += 4 * W) {
+                double fm[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) fm[i] = base + i * W < P.L.fat_cap ? c.fat[base + i * W].mass : 0.0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (fm[i] == 0) continue;
+                    const int s = base + i * W;
+                    const AgarFatPellet* f = &c.fat[s];
+                    if (!rect_hit(ra, rect_of(P.S, f->x, f->y, f->radius)) || !in_fov(f->x, f->y, f->radius, fx, fy, fov)) continue;
+                    consider(f->x, f->y, fm[i], ord0 + s);
+                }
+            }
         ord0 += P.L.fat_cap;
         const int K = P.L.n_players, cap = P.L.cell_cap;
         const uint16_t* live = live_cells(c, P);
