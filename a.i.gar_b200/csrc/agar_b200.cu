@@ -661,6 +661,9 @@ extern "C" int agar_create(const AgarConfig* cfg, int n_envs, int device, uint64
     P.n_envs = n_envs;
     P.rec_stride = (int)L.record_bytes + 8;
     P.full = e->full;
+    static_assert(AGAR_MAX_CELLS == 16, "cap_shift assumes cell_cap in {1, 16} (agar_layout.h)");
+    P.cap_shift = L.cell_cap == AGAR_MAX_CELLS ? 4 : 0;
+    P.g_magic = L.grid_squares > 1 ? (uint32_t)((1ull << 32) / (unsigned)L.grid_squares) + 1u : 0u;
     int vel_bytes = e->full ? L.n_players * L.cell_cap * 2 * 8 : 0;
     int obs_bytes = obs_scratch_bytes(L.grid_squares, e->full != 0);
     /* the pellet index (agar_dev.cuh) lives in the same scratch: it is built after the players have moved (velocities dead)

@@ -258,7 +258,7 @@ DEV void observe_agent(Ctx<W>& c, const DevParams& P, int k, int agent, float* o
         }
     }
     c.t.sync();
-    const Rect ra = rect_of(P.S, fx, fy, fov / 2);
+    const Rect ra = rect_of_call(P.S, fx, fy, fov / 2);
     /* channel slots in bot.py:458-495 order: PELLET, SELF, WALL, ENEMY, ALL_PLAYER, VIRUS, SELF_SLF, SELF_LF, ENEMY_SLF, ENEMY_LF */
     int ch = 0;
     const int ch_pel = cf.pellet_grid ? ch++ : -1;
@@ -275,7 +275,7 @@ DEV void observe_agent(Ctx<W>& c, const DevParams& P, int k, int agent, float* o
     /* square idx of the G x G view (bucket index uses G, not cols: the reference's shear when cols == G + 1): does it
      * show anything?  squares entirely outside the field do not (bot.py:392-393) */
     auto inside = [&](int idx) {
-        int cc = idx / G, r = idx - cc * G;
+        int cc = G > 1 ? (int)__umulhi((unsigned)idx, P.g_magic) : idx, r = idx - cc * G;
         double midx = sc.mid[r], midy = sc.mid[G + cc];
         return !(midx + gs / 2 < 0 || midx - gs / 2 > S || midy + gs / 2 < 0 || midy - gs / 2 > S);
     };
@@ -305,7 +305,7 @@ DEV void observe_agent(Ctx<W>& c, const DevParams& P, int k, int agent, float* o
                 const int sl = base + c.lane;
                 AgarFatPellet f = {};
                 if (sl < P.L.fat_cap) f = c.fat[sl];
-                const bool hit = f.mass != 0 && rect_hit(ra, rect_of(P.S, f.x, f.y, f.radius)) && in_fov(f.x, f.y, f.radius, fx, fy, fov);
+                const bool hit = f.mass != 0 && rect_hit(ra, rect_of_call(P.S, f.x, f.y, f.radius)) && in_fov(f.x, f.y, f.radius, fx, fy, fov);
                 unsigned hits = c.t.ballot(hit);
                 while (hits) {
                     const int b = __ffs((int)hits) - 1;
@@ -322,7 +322,7 @@ DEV void observe_agent(Ctx<W>& c, const DevParams& P, int k, int agent, float* o
         for (int idx = c.lane; idx < GG; idx += W) {
             if (obs && ch_pel >= 0) obs[ch_pel * GG + idx] = inside(idx) ? (float)sc.tab[idx] : 0.f;
             if (ch_wall >= 0) { /* bot.py:443-450 */
-                int cc = idx / G, r = idx - cc * G;
+                int cc = G > 1 ? (int)__umulhi((unsigned)idx, P.g_magic) : idx, r = idx - cc * G;
                 double midx = sc.mid[r], midy = sc.mid[G + cc];
                 double lb = py_minS(S, py_max0(midx - gs / 2)), tb = py_minS(S, py_max0(midy - gs / 2));
                 double rb = py_max0(py_minS(S, midx + gs / 2)), bb = py_max0(py_minS(S, midy + gs / 2));
@@ -340,12 +340,12 @@ DEV void observe_agent(Ctx<W>& c, const DevParams& P, int k, int agent, float* o
             const int n_it = c.n_live >= 0 ? c.n_live : K * cap;
             for (int t = c.lane; t < n_it; t += W) {
                 int idx = c.n_live >= 0 ? (int)live[t] : t;
-                int k2 = idx / cap, j = idx - k2 * cap;
+                int k2 = idx >> P.cap_shift, j = idx - (k2 << P.cap_shift);
                 if (j >= c.pl[k2].n_cells) continue;
                 const AgarCell* o = CELLP(c, P, k2, j);
                 if (k2 == k) {
                     if (!in_fov(o->x, o->y, o->radius, fx, fy, fov)) continue;
-                } else if (!(o->flags & AGAR_CF_INHASH) || !rect_hit(ra, rect_of(P.S, o->x, o->y, o->radius)) ||
+                } else if (!(o->flags & AGAR_CF_INHASH) || !rect_hit(ra, rect_of_call(P.S, o->x, o->y, o->radius)) ||
                            !in_fov(o->x, o->y, o->radius, fx, fy, fov))
                     continue;
                 if (o->mass > biggest) biggest = o->mass;
@@ -367,12 +367,12 @@ DEV void observe_agent(Ctx<W>& c, const DevParams& P, int k, int agent, float* o
             const int n_it = c.n_live >= 0 ? c.n_live : K * cap;
             for (int t = c.lane; t < n_it; t += W) {
                 int idx = c.n_live >= 0 ? (int)live[t] : t;
-                int k2 = idx / cap, j = idx - k2 * cap;
+                int k2 = idx >> P.cap_shift, j = idx - (k2 << P.cap_shift);
                 if ((!all && (k2 == k) != own) || j >= c.pl[k2].n_cells) continue;
                 const AgarCell* o = CELLP(c, P, k2, j);
                 if (k2 == k) {
                     if (!in_fov(o->x, o->y, o->radius, fx, fy, fov)) continue;
-                } else if (!(o->flags & AGAR_CF_INHASH) || !rect_hit(ra, rect_of(P.S, o->x, o->y, o->radius)) ||
+                } else if (!(o->flags & AGAR_CF_INHASH) || !rect_hit(ra, rect_of_call(P.S, o->x, o->y, o->radius)) ||
                            !in_fov(o->x, o->y, o->radius, fx, fy, fov))
                     continue;
                 unsigned long long bits = (unsigned long long)__double_as_longlong(o->mass);
@@ -404,7 +404,7 @@ DEV void observe_agent(Ctx<W>& c, const DevParams& P, int k, int agent, float* o
             if (c.lane == 0 && cf.virus_enabled)
                 for (int v = 0; v < c.h->n_viruses; ++v) {
                     const AgarMote* o = &c.vir[v];
-                    if (!(o->aux & AGAR_CF_INHASH) || !rect_hit(ra, rect_of(P.S, o->x, o->y, o->radius)) ||
+                    if (!(o->aux & AGAR_CF_INHASH) || !rect_hit(ra, rect_of_call(P.S, o->x, o->y, o->radius)) ||
                         !in_fov(o->x, o->y, o->radius, fx, fy, fov))
                         continue;
                     double orr = o->radius;
@@ -509,12 +509,12 @@ DEV void simple_state_agent(Ctx<W>& c, const DevParams& P, int k, float* obs) {
     double ed = 0.0;
     int eo = -1;
     {
-        const Rect ra = rect_of(P.S, fx, fy, fov / 2);
+        const Rect ra = rect_of_call(P.S, fx, fy, fov / 2);
         for (int idx = c.lane; idx < K * cap; idx += W) {
-            const int k2 = idx / cap, j = idx - k2 * cap;
+            const int k2 = idx >> P.cap_shift, j = idx - (k2 << P.cap_shift);
             if (k2 == k || j >= c.pl[k2].n_cells) continue;
             const AgarCell* o = CELLP(c, P, k2, j);
-            if (!(o->flags & AGAR_CF_INHASH) || !rect_hit(ra, rect_of(P.S, o->x, o->y, o->radius)) || !in_fov(o->x, o->y, o->radius, fx, fy, fov))
+            if (!(o->flags & AGAR_CF_INHASH) || !rect_hit(ra, rect_of_call(P.S, o->x, o->y, o->radius)) || !in_fov(o->x, o->y, o->radius, fx, fy, fov))
                 continue;
             const double d = (o->x - ox) * (o->x - ox) + (o->y - oy) * (o->y - oy); /* cell.py:158-160 */
             if (eo < 0 || d < ed) ed = d, eo = idx;
@@ -526,7 +526,7 @@ DEV void simple_state_agent(Ctx<W>& c, const DevParams& P, int k, float* obs) {
     int po = -1;
     {
         const double isz = (double)size;
-        const Rect ra = rect_of(P.S, fx, fy, isz / 2);
+        const Rect ra = rect_of_call(P.S, fx, fy, isz / 2);
         for (int s = c.lane; s < P.L.pellet_cap; s += W) {
             const uint32_t pk = c.pel[s];
             if (!pk) continue;
@@ -538,7 +538,7 @@ DEV void simple_state_agent(Ctx<W>& c, const DevParams& P, int k, float* obs) {
         for (int s = c.lane; s < P.L.fat_cap; s += W) {
             const AgarFatPellet* f = &c.fat[s];
             if (f->mass == 0) continue;
-            if (!rect_hit(ra, rect_of(P.S, f->x, f->y, f->radius)) || !in_fov(f->x, f->y, f->radius, fx, fy, isz)) continue;
+            if (!rect_hit(ra, rect_of_call(P.S, f->x, f->y, f->radius)) || !in_fov(f->x, f->y, f->radius, fx, fy, isz)) continue;
             const double d = (f->x - ox) * (f->x - ox) + (f->y - oy) * (f->y - oy);
             if (po < 0 || d < pd) pd = d, po = P.L.pellet_cap + s; /* a lane meets its integer pellets first: ascending canonical position */
         }
@@ -659,7 +659,7 @@ DEV void scripted_turn(Ctx<W>& c, const DevParams& P, int k) {
         for (int i = 1; i < p->n_cells; ++i)
             if (base[i].mass > base[big].mass) big = i;
         const double bxx = base[big].x, byy = base[big].y, bm = base[big].mass;
-        const Rect ra = rect_of(P.S, fx, fy, fov / 2);
+        const Rect ra = rect_of_call(P.S, fx, fy, fov / 2);
         /* argmax of mass / d^2 with first-max-wins in canonical order: order index = position in the candidate list */
         double best = -1.0, bestx = 0, besty = 0;
         int best_ord = 0x7fffffff;
@@ -688,7 +688,7 @@ DEV void scripted_turn(Ctx<W>& c, const DevParams& P, int k) {
                     if (fm[i] == 0) continue;
                     const int s = base + i * W;
                     const AgarFatPellet* f = &c.fat[s];
-                    if (!rect_hit(ra, rect_of(P.S, f->x, f->y, f->radius)) || !in_fov(f->x, f->y, f->radius, fx, fy, fov)) continue;
+                    if (!rect_hit(ra, rect_of_call(P.S, f->x, f->y, f->radius)) || !in_fov(f->x, f->y, f->radius, fx, fy, fov)) continue;
                     consider(f->x, f->y, fm[i], ord0 + s);
                 }
             }
@@ -698,10 +698,10 @@ DEV void scripted_turn(Ctx<W>& c, const DevParams& P, int k) {
         const int n_it = c.n_live >= 0 ? c.n_live : K * cap;
         for (int t = c.lane; t < n_it; t += W) {
             int idx = c.n_live >= 0 ? (int)live[t] : t;
-            int k2 = idx / cap, j = idx - k2 * cap;
+            int k2 = idx >> P.cap_shift, j = idx - (k2 << P.cap_shift);
             if (k2 == k || j >= c.pl[k2].n_cells) continue;
             const AgarCell* o = CELLP(c, P, k2, j);
-            if (!(o->flags & AGAR_CF_INHASH) || !rect_hit(ra, rect_of(P.S, o->x, o->y, o->radius)) ||
+            if (!(o->flags & AGAR_CF_INHASH) || !rect_hit(ra, rect_of_call(P.S, o->x, o->y, o->radius)) ||
                 !in_fov(o->x, o->y, o->radius, fx, fy, fov))
                 continue;
             if (bm > 1.25 * o->mass) consider(o->x, o->y, o->mass, ord0 + idx);
@@ -710,7 +710,7 @@ DEV void scripted_turn(Ctx<W>& c, const DevParams& P, int k) {
         if (P.cfg.virus_enabled)
             for (int v = c.lane; v < c.h->n_viruses; v += W) {
                 const AgarMote* o = &c.vir[v];
-                if (!(o->aux & AGAR_CF_INHASH) || !rect_hit(ra, rect_of(P.S, o->x, o->y, o->radius)) ||
+                if (!(o->aux & AGAR_CF_INHASH) || !rect_hit(ra, rect_of_call(P.S, o->x, o->y, o->radius)) ||
                     !in_fov(o->x, o->y, o->radius, fx, fy, fov))
                     continue;
                 if (bm > 1.25 * o->mass) consider(o->x, o->y, o->mass, ord0 + v);

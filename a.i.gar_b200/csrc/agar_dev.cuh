@@ -50,6 +50,8 @@ struct DevParams {
     /* optional per-launch outputs of the last bot turn ([E][A]); NULL = use agar_get */
     float* turn_reward;
     uint8_t* turn_done;
+    int cap_shift;               /* cell_cap is 1 or 16 (agar_layout.h): slot index -> (player, cell) by shift and mask           */
+    uint32_t g_magic;            /* floor(2^32 / G) + 1: idx / G == __umulhi(idx, g_magic) for idx < 2^16, G >= 2 (checked at create) */
     /* agar_step_host with pinned caller buffers: every CTA of the step launch exports its own envs' rows over PCIe as soon as
      * it has finished them (export_tail below); the last CTA raises a flag in host memory the caller polls */
     float* host_obs;             /* device-visible address of the caller's pinned observation buffer, or NULL           */
@@ -211,6 +213,20 @@ DEV double merge_time_for(double factor, double mass) { /* cell.py:154-155 */
     return factor * (25 + mass * 0.0233) * 30 / 2 / 1;
 }
 
+/* Out-of-line leaves for the multi-agent kernel.  Its frame body is ~13 000 hot SASS instructions (~200 KB, more than the SM's
+ * instruction cache: `stall_no_inst` was 20 % of the samples of the steady-state arena profile) and these three were inlined at
+ * 15 / 29 / 20+ places.  Scalar arguments and results only: nothing is forced into local memory at the call. */
+DEVN double radius_of_call(double m) { return radius_of(m); }
+DEVN uint32_t rect_of_packed(int S, double x, double y, double r) { /* bucket indices are -1 .. 52: one byte each, biased by 1 */
+    const Rect q = rect_of(S, x, y, r);
+    return (uint32_t)(q.x0 + 1) | (uint32_t)(q.x1 + 1) << 8 | (uint32_t)(q.y0 + 1) << 16 | (uint32_t)(q.y1 + 1) << 24;
+}
+DEV Rect rect_of_call(int S, double x, double y, double r) {
+    const uint32_t w = rect_of_packed(S, x, y, r);
+    Rect q;
+    q.x0 = (int)(w & 0xffu) - 1, q.x1 = (int)(w >> 8 & 0xffu) - 1, q.y0 = (int)(w >> 16 & 0xffu) - 1, q.y1 = (int)(w >> 24) - 1;
+    return q;
+}
 /* numpy pairwise summation order for n <= 16 (oracle np_sum) */
 template <class F>
 DEV double np_sum(F get, int n) {
@@ -229,6 +245,13 @@ DEV double np_sum(F get, int n) {
     double res = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
     for (; i < n; ++i) res += get(i);
     return res;
+}
+
+/* the three sums over a player's cells (total mass, mass-weighted x / y: player.py:129-161), out of line — see above */
+DEVN double cells_np_sum(const AgarCell* base, int n, int what) {
+    if (what == 0) return np_sum([&](int i) { return base[i].mass; }, n);
+    if (what == 1) return np_sum([&](int i) { return base[i].x * base[i].mass; }, n);
+    return np_sum([&](int i) { return base[i].y * base[i].mass; }, n);
 }
 
 /* ------------------------------------------------------------------ Philox4x32-10 (oracle/philox.py) */
@@ -290,7 +313,7 @@ DEV double total_mass(const Ctx<W>& c, const DevParams& P, int k) {
     int n = c.pl[k].n_cells;
     if (n == 0) return 0.0;
     const AgarCell* base = CELLP(c, P, k, 0);
-    return np_sum([&](int i) { return base[i].mass; }, n);
+    return cells_np_sum(base, n, 0);
 }
 /* lane 0: getFovPos + getFovSize, caches in the player */
 template <int W>
@@ -301,8 +324,8 @@ DEV void update_fov(Ctx<W>& c, const DevParams& P, int k) {
     const AgarCell* base = CELLP(c, P, k, 0);
     double tm = total_mass(c, P, k);
     if (tm != 0) {
-        p->fov_x = np_sum([&](int i) { return base[i].x * base[i].mass; }, n) / tm;
-        p->fov_y = np_sum([&](int i) { return base[i].y * base[i].mass; }, n) / tm;
+        p->fov_x = cells_np_sum(base, n, 1) / tm;
+        p->fov_y = cells_np_sum(base, n, 2) / tm;
         p->fov_valid = 1;
     }
     double rmax = base[0].radius;
@@ -329,7 +352,7 @@ DEV void build_live_cells(Ctx<W>& c, const DevParams& P) {
     const int cap = P.L.cell_cap, total = P.L.n_players * cap;
     int n = 0;
     for (int base = 0; base < total; base += W) {
-        int idx = base + c.lane, k2 = idx / cap, j = idx - k2 * cap;
+        int idx = base + c.lane, k2 = idx >> P.cap_shift, j = idx - (k2 << P.cap_shift);
         bool on = idx < total && j < c.pl[k2].n_cells;
         unsigned b = c.t.ballot(on);
         if (on) live[n + __popc(b & ((1u << c.lane) - 1))] = (uint16_t)idx;
@@ -353,7 +376,7 @@ DEV AgarCell* cell_append(Ctx<W>& c, const DevParams& P, int k, double x, double
     AgarCell* nc = CELLP(c, P, k, p->n_cells);
     AgarCell z = {};
     *nc = z;
-    nc->x = x, nc->y = y, nc->mass = mass, nc->radius = radius_of(mass);
+    nc->x = x, nc->y = y, nc->mass = mass, nc->radius = radius_of_call(mass);
     nc->uid = c.h->next_uid++;
     p->n_cells += 1;
     return nc;
@@ -412,7 +435,7 @@ DEV bool player_bucket_occupied(const Ctx<W>& c, const DevParams& P, int bx, int
         for (int i = 0; i < c.pl[k].n_cells; ++i) {
             const AgarCell* q = CELLP(c, P, k, i);
             if (!(q->flags & AGAR_CF_INHASH)) continue;
-            Rect r = rect_of(P.S, q->x, q->y, q->radius);
+            Rect r = rect_of_call(P.S, q->x, q->y, q->radius);
             if (r.x1 < r.x0 || r.y1 < r.y0) continue;
             if (bx >= r.x0 && bx <= r.x1 && by >= r.y0 && by <= r.y1) return true;
         }
@@ -496,7 +519,7 @@ DEV void spawn_viruses(Ctx<W>& c, const DevParams& P) { /* lane 0; :262-275 */
         AgarMote* v = &c.vir[c.h->n_viruses];
         AgarMote z = {};
         *v = z;
-        v->x = x, v->y = y, v->mass = 100.0, v->radius = radius_of(100.0);
+        v->x = x, v->y = y, v->mass = 100.0, v->radius = radius_of_call(100.0);
         log_ev(c, P, AGAR_EV_SPAWN_VIRUS, c.h->n_viruses, (int)x, (int)y, 0);
         c.h->n_viruses += 1;
     }
@@ -637,7 +660,7 @@ DEVN void player_split_and_flags(Ctx<W>& c, const DevParams& P, int k, double* v
                 add_momentum(S, nc->x, nc->y, xp, yp, parent_radius, &nc->svx, &nc->svy, &nc->counter);
                 nc->merge_time = merge_time_for(1, nc->mass);
                 q->mass = q->mass / 2;
-                q->radius = radius_of(q->mass);
+                q->radius = radius_of_call(q->mass);
                 log_ev(c, P, AGAR_EV_SPLIT, k, (int)q->uid, (int)nc->uid, 0);
             }
         }
@@ -666,7 +689,7 @@ DEVN void player_ejections(Ctx<W>& c, const DevParams& P, int k) {
             AgarMote* b = &c.blob[c.h->n_blobs];
             AgarMote z = {};
             *b = z;
-            b->x = q->x, b->y = q->y, b->mass = P.blob_mass, b->radius = radius_of(P.blob_mass);
+            b->x = q->x, b->y = q->y, b->mass = P.blob_mass, b->radius = radius_of_call(P.blob_mass);
             add_momentum(S, b->x, b->y, p->cmd_x, p->cmd_y, q->radius, &b->svx, &b->svy, &b->counter);
             b->aux = q->uid;
             log_ev(c, P, AGAR_EV_EJECT, k, (int)q->uid, c.h->n_blobs, 0);
@@ -798,7 +821,7 @@ DEV void cell_kinematics(const DevParams& P, AgarCell* q, double cmd_x, double c
     double mass = q->mass, radius = q->radius;
     if (mass >= 4) {
         mass = mass * P.decay_rate;
-        radius = radius_of(mass);
+        radius = radius_of_call(mass);
         q->mass = mass, q->radius = radius;
     }
     double svx = q->svx, svy = q->svy;
@@ -837,7 +860,7 @@ DEV void update_players(Ctx<W>& c, const DevParams& P) {
     double* vel = (double*)c.scratch; /* [K][2][cap] */
     /* phase A: every live cell of every live player, lane-parallel */
     for (int idx = c.lane; idx < K * cap; idx += W) {
-        int k = idx / cap, i = idx - k * cap;
+        int k = idx >> P.cap_shift, i = idx - (k << P.cap_shift);
         const AgarPlayer* p = &c.pl[k];
         if (!p->alive || i >= p->n_cells) continue;
         double vx, vy;
@@ -877,7 +900,7 @@ DEV void update_players(Ctx<W>& c, const DevParams& P) {
     c.t.sync();
     /* updateHashTables: every live cell / virus is (re)inserted */
     for (int idx = c.lane; idx < K * cap; idx += W) {
-        int k = idx / cap, i = idx - k * cap;
+        int k = idx >> P.cap_shift, i = idx - (k << P.cap_shift);
         if (i < c.pl[k].n_cells) CELLP(c, P, k, i)->flags |= AGAR_CF_INHASH;
     }
     for (int i = c.lane; i < c.h->n_viruses; i += W) c.vir[i].aux = AGAR_CF_INHASH;
@@ -936,7 +959,7 @@ DEVN void virus_blob_overlap_seq(Ctx<W>& c, const DevParams& P) {
     const double S = (double)P.S;
     for (int vi = 0; vi < c.h->n_viruses; ++vi) {
         AgarMote* v = &c.vir[vi];
-        Rect rv = rect_of(P.S, v->x, v->y, v->radius);
+        Rect rv = rect_of_call(P.S, v->x, v->y, v->radius);
         /* candidates are the blobs sharing a bucket with the virus BEFORE it eats; kept as a bitmask walk */
         int nb0 = c.h->n_blobs;
         int removed_before = 0;
@@ -944,7 +967,7 @@ DEVN void virus_blob_overlap_seq(Ctx<W>& c, const DevParams& P) {
             int b = b0 - removed_before;
             AgarMote* bl = &c.blob[b];
             /* rect test uses the virus rectangle at the start of its pass (rv) */
-            if (!rect_hit(rv, rect_of(P.S, bl->x, bl->y, bl->radius))) continue;
+            if (!rect_hit(rv, rect_of_call(P.S, bl->x, bl->y, bl->radius))) continue;
             if (!overlap(v->x, v->y, v->mass, v->radius, bl->x, bl->y, bl->mass, bl->radius)) continue;
             double bx = bl->x, by = bl->y;
             grow_mote(v, bl->mass);
@@ -959,13 +982,13 @@ DEVN void virus_blob_overlap_seq(Ctx<W>& c, const DevParams& P) {
                     AgarMote* nv = &c.vir[c.h->n_viruses];
                     AgarMote z = {};
                     *nv = z;
-                    nv->x = v->x, nv->y = v->y, nv->mass = v->mass / 2, nv->radius = radius_of(nv->mass);
+                    nv->x = v->x, nv->y = v->y, nv->mass = v->mass / 2, nv->radius = radius_of_call(nv->mass);
                     double cs, sn;
                     agar_dir(oy - nv->y, ox - nv->x, &cs, &sn);
                     double xp = cs * nv->radius * 4.5 + v->x, yp = sn * nv->radius * 4.5 + v->y;
                     add_momentum(S, nv->x, nv->y, xp, yp, v->radius, &nv->svx, &nv->svy, &nv->counter);
                     v->mass = v->mass / 2;
-                    v->radius = radius_of(v->mass);
+                    v->radius = radius_of_call(v->mass);
                     c.h->n_viruses += 1;
                     split = 1;
                 }
@@ -1005,13 +1028,13 @@ DEVN void player_virus_overlap_seq(Ctx<W>& c, const DevParams& P) {
         if (!p->alive) continue;
         for (int ci = 0; ci < p->n_cells; ++ci) {
             AgarCell* q = CELLP(c, P, k, ci);
-            Rect rc = rect_of(P.S, q->x, q->y, q->radius);
+            Rect rc = rect_of_call(P.S, q->x, q->y, q->radius);
             /* candidate set fixed at the start of the cell's pass: bit v0 of a 64-bit mask over the virus list */
             unsigned long long cand = 0;
             int nv0 = c.h->n_viruses;
             for (int v = 0; v < nv0 && v < 64; ++v)
                 if ((c.vir[v].aux & AGAR_CF_INHASH) &&
-                    rect_hit(rc, rect_of(P.S, c.vir[v].x, c.vir[v].y, c.vir[v].radius)))
+                    rect_hit(rc, rect_of_call(P.S, c.vir[v].x, c.vir[v].y, c.vir[v].radius)))
                     cand |= 1ull << v;
             int removed = 0;
             for (int v0 = 0; v0 < nv0 && v0 < 64; ++v0) {
@@ -1120,7 +1143,7 @@ DEV bool cell_eats_pellets_indexed(Ctx<W>& c, const DevParams& P, int k, int ci,
         total = cg::reduce(c.t, total, cg::plus<int>());
         m_max = cm + 3.0 * total;
         if (!(m_max < AG_MAX_MASS)) m_max = AG_MAX_MASS;
-        r_max = radius_of(m_max);
+        r_max = radius_of_call(m_max);
         if (r_max < cr) r_max = cr; /* after an eject the stored radius is STALE (larger than sqrt(mass / pi), cell.py:92) until the
                                      * next decay; the first tests of the chain use it as it is */
         if ((int)r_max + 2 <= R) break;
@@ -1165,7 +1188,7 @@ DEV bool cell_eats_pellets_indexed(Ctx<W>& c, const DevParams& P, int k, int ci,
             double nm = cm + (double)pm;
             if (!(nm < AG_MAX_MASS)) nm = AG_MAX_MASS;
             cm = nm;
-            cr = radius_of(nm);
+            cr = radius_of_call(nm);
             c.t.sync(); /* every lane has read the slot */
             if (c.lane == 0) {
                 log_ev(c, P, AGAR_EV_EAT_PELLET, k, (int)uid, first, 0);
@@ -1188,7 +1211,7 @@ DEV bool cell_may_eat(const Ctx<W>& c, const DevParams& P, int k, int ci, const 
     const AgarCell* q = CELLP(c, P, k, ci);
     const double cx = q->x, cy = q->y, cm = q->mass, cr = q->radius;
     if (fat_unknown) return true;
-    const Rect rc = rect_of(P.S, cx, cy, cr);
+    const Rect rc = rect_of_call(P.S, cx, cy, cr);
     const double fat_mass = (double)n_fatl * P.blob_mass * 1.000001;
     int R = (int)cr + 2, bx0, bx1, by0, by1;
     double m_max, r_max;
@@ -1204,7 +1227,7 @@ DEV bool cell_may_eat(const Ctx<W>& c, const DevParams& P, int k, int ci, const 
         }
         m_max = cm + 3.0 * total + fat_mass;
         if (!(m_max < AG_MAX_MASS)) m_max = AG_MAX_MASS;
-        r_max = radius_of(m_max);
+        r_max = radius_of_call(m_max);
         if (r_max < cr) r_max = cr;
         if ((int)r_max + 2 <= R) break;
         R = (int)r_max + 2;
@@ -1227,7 +1250,7 @@ DEV bool cell_may_eat(const Ctx<W>& c, const DevParams& P, int k, int ci, const 
         if (fm == 0) continue;
         const double dx = cx - f->x, dy = cy - f->y;
         const double reach2 = (fr * fr > rr ? fr * fr * (1.0 + 1e-9) : rr);
-        if ((dx * dx + dy * dy) * 1.1 < reach2 && m_max > 1.25 * fm && rect_hit(rc, rect_of(P.S, f->x, f->y, fr))) return true;
+        if ((dx * dx + dy * dy) * 1.1 < reach2 && m_max > 1.25 * fm && rect_hit(rc, rect_of_call(P.S, f->x, f->y, fr))) return true;
     }
     return false;
 }
@@ -1239,7 +1262,7 @@ template <int W>
 DEV void cell_eats_pellets(Ctx<W>& c, const DevParams& P, int k, int ci, bool fat_too, bool indexed = false) {
     AgarCell* q = CELLP(c, P, k, ci);
     double cx = q->x, cy = q->y, cm = q->mass, cr = q->radius;
-    const Rect rc = rect_of(P.S, cx, cy, cr); /* candidates are fixed before the cell grows */
+    const Rect rc = rect_of_call(P.S, cx, cy, cr); /* candidates are fixed before the cell grows */
     const bool by_index = W == 32 && indexed && cell_eats_pellets_indexed(c, P, k, ci, rc, cm, cr, q->uid);
     const int cap = by_index ? 0 : P.L.pellet_cap; /* the index served this cell: no scan of the pool */
     /* Integer window: a pellet can only be eaten if it lies within the cell's radius, and within one chunk of W
@@ -1270,7 +1293,7 @@ DEV void cell_eats_pellets(Ctx<W>& c, const DevParams& P, int k, int ci, bool fa
             double nm = cm + (double)em;
             if (!(nm < AG_MAX_MASS)) nm = AG_MAX_MASS;
             cm = nm;
-            cr = radius_of(nm);
+            cr = radius_of_call(nm);
             if (c.lane == 0) {
                 log_ev(c, P, AGAR_EV_EAT_PELLET, k, (int)q->uid, base + l, 0);
                 c.pel[base + l] = 0;
@@ -1286,7 +1309,7 @@ DEV void cell_eats_pellets(Ctx<W>& c, const DevParams& P, int k, int ci, bool fa
             int s = base + c.lane;
             double fx = 0, fy = 0, fm = 0, fr = 0;
             if (s < fcap) fx = c.fat[s].x, fy = c.fat[s].y, fm = c.fat[s].mass, fr = c.fat[s].radius;
-            bool cand = fm != 0 && rect_hit(rc, rect_of(P.S, fx, fy, fr));
+            bool cand = fm != 0 && rect_hit(rc, rect_of_call(P.S, fx, fy, fr));
             unsigned done_mask = 0;
             while (true) {
                 bool hit = cand && overlap(cx, cy, cm, cr, fx, fy, fm, fr) && cm > 1.25 * fm;
@@ -1297,7 +1320,7 @@ DEV void cell_eats_pellets(Ctx<W>& c, const DevParams& P, int k, int ci, bool fa
                 double nm = cm + em;
                 if (!(nm < AG_MAX_MASS)) nm = AG_MAX_MASS;
                 cm = nm;
-                cr = radius_of(nm);
+                cr = radius_of_call(nm);
                 if (c.lane == 0) {
                     log_ev(c, P, AGAR_EV_EAT_PELLET, k, (int)q->uid, (base + l) | 0x10000, 0);
                     AgarFatPellet z = {};
@@ -1320,12 +1343,12 @@ DEVN void player_blob_overlap_seq(Ctx<W>& c, const DevParams& P) {
         if (!p->alive) continue;
         for (int ci = 0; ci < p->n_cells; ++ci) {
             AgarCell* q = CELLP(c, P, k, ci);
-            Rect rc = rect_of(P.S, q->x, q->y, q->radius);
+            Rect rc = rect_of_call(P.S, q->x, q->y, q->radius);
             int nb0 = c.h->n_blobs, removed = 0;
             for (int b0 = 0; b0 < nb0; ++b0) {
                 int bi = b0 - removed;
                 AgarMote* b = &c.blob[bi];
-                if (!rect_hit(rc, rect_of(P.S, b->x, b->y, b->radius))) continue;
+                if (!rect_hit(rc, rect_of_call(P.S, b->x, b->y, b->radius))) continue;
                 if (overlap(q->x, q->y, q->mass, q->radius, b->x, b->y, b->mass, b->radius) && b->aux != q->uid &&
                     q->mass > 1.25 * b->mass) {
                     log_ev(c, P, AGAR_EV_EAT_BLOB, k, (int)q->uid, bi, (int)b->aux);
@@ -1346,7 +1369,7 @@ DEVN bool player_player_one_cell(Ctx<W>& c, const DevParams& P, int k, int ci) {
     const int K = P.L.n_players;
     AgarCell* q = CELLP(c, P, k, ci);
     uint32_t my_uid = q->uid;
-    Rect rc = rect_of(P.S, q->x, q->y, q->radius);
+    Rect rc = rect_of_call(P.S, q->x, q->y, q->radius);
     /* candidate snapshot: per enemy player a 16-bit mask over its cell list, taken before any eating;
      * enemy lists only shrink by this cell's own eating, tracked with `removed` per player */
     for (int k2 = 0; k2 < K; ++k2) {
@@ -1356,7 +1379,7 @@ DEVN bool player_player_one_cell(Ctx<W>& c, const DevParams& P, int k, int ci) {
         unsigned cand = 0;
         for (int j = 0; j < n2; ++j) {
             const AgarCell* o = CELLP(c, P, k2, j);
-            if ((o->flags & AGAR_CF_INHASH) && rect_hit(rc, rect_of(P.S, o->x, o->y, o->radius))) cand |= 1u << j;
+            if ((o->flags & AGAR_CF_INHASH) && rect_hit(rc, rect_of_call(P.S, o->x, o->y, o->radius))) cand |= 1u << j;
         }
         int removed = 0;
         for (int j0 = 0; j0 < n2; ++j0) {
@@ -1393,16 +1416,16 @@ DEV void player_player_overlap_seq(Ctx<W>& c, const DevParams& P) {
         for (int ci = 0; ci < c.pl[k].n_cells; ++ci) {
             const AgarCell* q = CELLP(c, P, k, ci);
             const double qx = q->x, qy = q->y, qm = q->mass, qr = q->radius;
-            const Rect rc = rect_of(P.S, qx, qy, qr);
+            const Rect rc = rect_of_call(P.S, qx, qy, qr);
             const uint16_t* live = live_cells(c, P);
             const int n_it = c.n_live >= 0 ? c.n_live : K * cap;
             bool hit = false;
             for (int t = c.lane; t < n_it && !hit; t += W) {
                 const int idx = c.n_live >= 0 ? (int)live[t] : t;
-                const int k2 = idx / cap, j = idx - k2 * cap;
+                const int k2 = idx >> P.cap_shift, j = idx - (k2 << P.cap_shift);
                 if (k2 == k || j >= c.pl[k2].n_cells) continue;
                 const AgarCell* o = CELLP(c, P, k2, j);
-                if ((o->flags & AGAR_CF_INHASH) && rect_hit(rc, rect_of(P.S, o->x, o->y, o->radius)) &&
+                if ((o->flags & AGAR_CF_INHASH) && rect_hit(rc, rect_of_call(P.S, o->x, o->y, o->radius)) &&
                     overlap(qx, qy, qm, qr, o->x, o->y, o->mass, o->radius))
                     hit = true;
             }
@@ -1427,7 +1450,7 @@ DEV bool any_player_mote_hit(Ctx<W>& c, const DevParams& P, const AgarMote* mote
     if (n > 0)
         for (int t = c.lane; t < n_it && !hit; t += W) {
             int idx = c.n_live >= 0 ? (int)live[t] : t;
-            int k = idx / cap, i = idx - k * cap;
+            int k = idx >> P.cap_shift, i = idx - (k << P.cap_shift);
             if (!c.pl[k].alive || i >= c.pl[k].n_cells) continue;
             const AgarCell* q = CELLP(c, P, k, i);
             for (int v = 0; v < n; ++v) {
@@ -1449,7 +1472,7 @@ DEV bool any_player_player_hit(Ctx<W>& c, const DevParams& P) {
     const int n_it = c.n_live >= 0 ? c.n_live : K * cap;
     for (int t = c.lane; t < n_it && !hit; t += W) {
         int idx = c.n_live >= 0 ? (int)live[t] : t;
-        int k = idx / cap, i = idx - k * cap;
+        int k = idx >> P.cap_shift, i = idx - (k << P.cap_shift);
         if (!c.pl[k].alive || i >= c.pl[k].n_cells) continue;
         const AgarCell* q = CELLP(c, P, k, i);
         for (int k2 = k + 1; k2 < K && !hit; ++k2) {
@@ -1536,13 +1559,13 @@ DEV void field_update_phase(Ctx<W>& c, const DevParams& P, int phase) {
                 for (int base = 0; base < n_live; base += W) {
                     const int t = base + c.lane;
                     const int idx = t < n_live ? (int)live[t] : 0;
-                    const bool may = t < n_live && cell_may_eat(c, P, idx / cap_c, idx % cap_c, fatlist, fat_unknown ? 0 : n_fatl, fat_unknown);
+                    const bool may = t < n_live && cell_may_eat(c, P, idx >> P.cap_shift, idx & (cap_c - 1), fatlist, fat_unknown ? 0 : n_fatl, fat_unknown);
                     unsigned todo = c.t.ballot(may);
                     while (todo) { /* canonical order: ascending (player, cell) */
                         const int l = __ffs(todo) - 1;
                         todo &= todo - 1;
                         const int id = c.t.shfl(idx, l);
-                        cell_eats_pellets(c, P, id / cap_c, id % cap_c, fat_too && c.h->n_fat > 0, true);
+                        cell_eats_pellets(c, P, id >> P.cap_shift, id & (cap_c - 1), fat_too && c.h->n_fat > 0, true);
                     }
                 }
                 c.n_live = -1;
