@@ -608,7 +608,8 @@ extern "C" int agar_set_tile_width(AgarEnv* e, int W) {
             e->sp.grid_off = tail_words * 4;
             e->sp.strideB = ((tail_words + gg) | 1) * 4;
         }
-        if (e->L.pellet_cap > 128 * W) return fail(e, AGAR_E_UNSUPPORTED, "pellet pool too large for this tile width%s", "");
+        if (e->L.pellet_cap > (W >= 4 ? 64 : 128) * W) /* two mask words per lane: SMask<W>, agar_simple.cuh */
+            return fail(e, AGAR_E_UNSUPPORTED, "pellet pool too large for this tile width%s", "");
         int threads = 128; /* measured (round 2, exact libm arithmetic): four warps per CTA beat two at every batch size (4096 envs: 7.7e8 vs 7.0e8) */
         const char* tenv = getenv("AGAR_SIMPLE_THREADS");
         if (tenv && atoi(tenv) >= 32) threads = atoi(tenv) / 32 * 32;

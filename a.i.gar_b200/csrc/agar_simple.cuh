@@ -191,6 +191,27 @@ DEV void s_set_command_point(SReg& r, const DevParams& P, double a0, double a1, 
     r.cmd_y = top + a1 * size;
 }
 
+/* Candidate masks of the two pellet loops (observation, eating): bit j of word 0 / word 1 <-> slot sub + W * j / sub + W * (MB + j).
+ * Tiles of >= 4 lanes hold at most 64 slots per lane (agar_set_tile_width checks pellet_cap <= 64 W) and keep 32-bit words — the
+ * 64-bit shifts / find-first-set of the wide form were 9 % of k_simple<8>'s instructions; 1- and 2-lane tiles keep 64-bit words. */
+template <int W>
+struct SMask {
+    typedef uint32_t T;
+    static constexpr int MB = 32;
+};
+template <>
+struct SMask<1> {
+    typedef unsigned long long T;
+    static constexpr int MB = 64;
+};
+template <>
+struct SMask<2> {
+    typedef unsigned long long T;
+    static constexpr int MB = 64;
+};
+DEV int s_ffs(uint32_t m) { return __ffs((int)m); }
+DEV int s_ffs(unsigned long long m) { return __ffsll((long long)m); }
+
 /* bot.py:326-497 for the pellet channel.  Warp-uniform: every lane calls it; `mine` = this tile observes now.
  * row: this env's observation row in the caller's buffer (nullptr: a decision inside a multi-frame step, nobody
  * reads the grid — only the fov caches advance, as in the reference). */
@@ -239,22 +260,24 @@ DEV void s_observe(SReg& r, const SPtr& q, const DevParams& P, bool mine, float*
         /* integer window that contains every pellet in_fov() can accept (radius < 1) */
         const int wx0 = (int)floor(xmin) - 1, wx1 = (int)ceil(xmax) + 1, wy0 = (int)floor(ymin) - 1, wy1 = (int)ceil(ymax) + 1;
         /* phase 1: integer window -> candidate bitmask over this lane's slots (converged, cheap) */
-        unsigned long long m0 = 0, m1 = 0;
+        typedef typename SMask<W>::T MT;
+        constexpr int MB = SMask<W>::MB;
+        MT m0 = 0, m1 = 0;
         {
-            const int cap = P.L.pellet_cap, split = min(cap, sub + 64 * W);
+            const int cap = P.L.pellet_cap, split = min(cap, sub + MB * W);
             int j = 0;
             for (int s = sub; s < split; s += W, ++j) { /* branch-free accumulation, two plain loops */
                 uint32_t pk = q.pel[s];
                 int px = AGAR_PELLET_X(pk), py = AGAR_PELLET_Y(pk);
                 bool in = px >= wx0 && px <= wx1 && py >= wy0 && py <= wy1 && pk != 0;
-                m0 |= (unsigned long long)in << j;
+                m0 |= (MT)in << j;
             }
             j = 0;
-            for (int s = sub + 64 * W; s < cap; s += W, ++j) {
+            for (int s = sub + MB * W; s < cap; s += W, ++j) {
                 uint32_t pk = q.pel[s];
                 int px = AGAR_PELLET_X(pk), py = AGAR_PELLET_Y(pk);
                 bool in = px >= wx0 && px <= wx1 && py >= wy0 && py <= wy1 && pk != 0;
-                m1 |= (unsigned long long)in << j;
+                m1 |= (MT)in << j;
             }
         }
         /* phase 2: every lane bins its own next candidate per iteration.  The body is straight-line (predicated REDs,
@@ -265,10 +288,10 @@ DEV void s_observe(SReg& r, const SPtr& q, const DevParams& P, bool mine, float*
         while (m0 | m1) {
             int j;
             if (m0) {
-                j = __ffsll((long long)m0) - 1;
+                j = s_ffs(m0) - 1;
                 m0 &= m0 - 1;
             } else {
-                j = 64 + __ffsll((long long)m1) - 1;
+                j = MB + s_ffs(m1) - 1;
                 m1 &= m1 - 1;
             }
             uint32_t pk = q.pel[sub + W * j];
@@ -348,37 +371,38 @@ DEV void s_field_update(SReg& r, const SPtr& q, const DevParams& P, uint32_t env
      * eaten ones, in ascending order — remember up to four and skip the free-slot search when respawning. */
     const bool pool_full = r.n_pellets == cap;
     int eaten0 = S_NONE, eaten1 = S_NONE, eaten2 = S_NONE, eaten3 = S_NONE, n_eaten = 0;
-    unsigned long long m0 = 0, m1 = 0; /* bit j <-> slot sub + W*j */
+    typedef typename SMask<W>::T MT;
+    constexpr int MB = SMask<W>::MB;
+    MT m0 = 0, m1 = 0; /* bit j <-> slot sub + W * j (m0), sub + W * (MB + j) (m1) */
     auto scan = [&](int first_slot) {
         m0 = m1 = 0;
-        const int split = min(cap, sub + 64 * W);
+        const int split = min(cap, sub + MB * W);
         const unsigned r2 = (unsigned)(2 * reach);
         int j = 0;
         for (int s = sub; s < split; s += W, ++j) { /* branch-free accumulation, two plain loops */
             uint32_t pk = q.pel[s];
             int px = AGAR_PELLET_X(pk), py = AGAR_PELLET_Y(pk);
             bool in = (unsigned)(px - icx + reach) <= r2 && (unsigned)(py - icy + reach) <= r2 && pk != 0 && s >= first_slot;
-            m0 |= (unsigned long long)in << j;
+            m0 |= (MT)in << j;
         }
         j = 0;
-        for (int s = sub + 64 * W; s < cap; s += W, ++j) {
+        for (int s = sub + MB * W; s < cap; s += W, ++j) {
             uint32_t pk = q.pel[s];
             int px = AGAR_PELLET_X(pk), py = AGAR_PELLET_Y(pk);
             bool in = (unsigned)(px - icx + reach) <= r2 && (unsigned)(py - icy + reach) <= r2 && pk != 0 && s >= first_slot;
-            m1 |= (unsigned long long)in << j;
+            m1 |= (MT)in << j;
         }
     };
     scan(0);
-    while (true) {
-        int mine = m0 ? sub + W * (__ffsll((long long)m0) - 1) : (m1 ? sub + W * (64 + __ffsll((long long)m1) - 1) : S_NONE);
+    while (s_any<W>((m0 | m1) != 0)) { /* one vote decides the (usual) frame without candidates: no find-first-set, no tile minimum */
+        int mine = m0 ? sub + W * (s_ffs(m0) - 1) : (m1 ? sub + W * (MB + s_ffs(m1) - 1) : S_NONE);
         int first = tile_min<W>(mine);
-        if (!s_any<W>(first != S_NONE)) break;
         if (first != S_NONE && mine == first) { /* owner lane drops the candidate */
             int j = (first - sub) / W;
-            if (j < 64)
-                m0 &= ~(1ull << j);
+            if (j < MB)
+                m0 &= ~((MT)1 << j);
             else
-                m1 &= ~(1ull << (j - 64));
+                m1 &= ~((MT)1 << (j - MB));
         }
         const uint32_t pk = q.pel[first != S_NONE ? first : 0];
         s_sync<W>(); /* every lane has read its tile's candidate before lane sub == 0 may clear the slot */

@@ -51,6 +51,8 @@ VARIATIONS = [
     (dict(num_nn=2, num_greedy=1, virus=True, split=True, eject=True, overrides={"normalize_grid_by_max_mass": 1}), 32),
     (dict(num_nn=1, num_greedy=1, split=True, overrides={"normalize_grid_by_max_mass": 1, "all_player_grid": 1, "self_grid": 0, "enemy_grid": 0,
                                                          "self_grid_lf": 0, "enemy_grid_lf": 0}), 16),
+    # spare pellet slots (never refilled, field.py:65): the second candidate-mask word of the register-resident kernel
+    (dict(overrides={"pellet_cap": 200}), 4), (dict(overrides={"pellet_cap": 100}), 2),
     # GRID_VIEW_ENABLED = False: Bot.getSimpleStateRepresentation (bot.py:511-548), every tile width of the general kernel
     (dict(grid_view=False), None), (dict(grid_view=False), 8),
     (dict(num_nn=1, num_greedy=1, virus=True, split=True, eject=True, grid_view=False), 32),
