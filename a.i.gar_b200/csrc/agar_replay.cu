@@ -225,12 +225,27 @@ __global__ void k_rp_per_sample(ReplayDev d, const double* __restrict__ u, int b
         weights[i] = agar_pow(p_sample * len, -d.beta) / max_weight;
     }
 }
-__global__ void k_rp_set_priorities(ReplayDev d, const int32_t* __restrict__ idx, const double* __restrict__ prio, int batch) {
+/* staged != 0: the launch carries batch * 4 bytes of dynamic shared memory and every CTA keeps a copy of idx there — the
+ * "does a later entry name the same leaf" scan then runs on shared memory without an early exit (consecutive threads read
+ * consecutive words): 2048 entries 123 us -> a few us */
+__global__ void k_rp_set_priorities(ReplayDev d, const int32_t* __restrict__ idx, const double* __restrict__ prio, int batch, int staged) {
+    extern __shared__ int32_t sh_idx[];
+    if (staged) {
+        for (int j = threadIdx.x; j < batch; j += blockDim.x) sh_idx[j] = idx[j];
+        __syncthreads();
+    }
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= batch) return;
     /* duplicates in idx: the reference applies them in order, the last one wins */
-    for (int j = i + 1; j < batch; ++j)
-        if (idx[j] == idx[i]) return;
+    if (staged) {
+        const int32_t mine = sh_idx[i];
+        bool later = false;
+        for (int j = i + 1; j < batch; ++j) later |= sh_idx[j] == mine;
+        if (later) return;
+    } else {
+        for (int j = i + 1; j < batch; ++j)
+            if (idx[j] == idx[i]) return;
+    }
     /* replay_buffer.py:203-204 asserts priority > 0 and 0 <= idx < len(storage): skip and flag instead of poisoning the trees */
     if (idx[i] < 0 || idx[i] >= d.counters[1]) {
         atomicOr(&d.counters[3], AGAR_RP_ERR_INDEX);
@@ -244,11 +259,22 @@ __global__ void k_rp_set_priorities(ReplayDev d, const int32_t* __restrict__ idx
     d.sum[d.itcap + idx[i]] = v;
     d.mn[d.itcap + idx[i]] = v;
 }
-__global__ void k_rp_max_priority(ReplayDev d, const double* __restrict__ prio, int batch) {
-    double m = *d.max_priority;
-    for (int i = 0; i < batch; ++i)
-        if (prio[i] > m && prio[i] <= 1.7e308) m = prio[i];
-    *d.max_priority = m;
+/* _max_priority = max(_max_priority, priority) over the batch (replay_buffer.py:188): a maximum, so any order — one CTA, strided
+ * loads and a shared-memory tree (a lone thread walking 2048 priorities took 190 us of a 750 us learner tick) */
+__global__ void __launch_bounds__(256) k_rp_max_priority(ReplayDev d, const double* __restrict__ prio, int batch) {
+    __shared__ double sm[256];
+    double m = 0.0; /* priorities are > 0 (guarded by k_rp_set_priorities) */
+    for (int i = threadIdx.x; i < batch; i += 256) {
+        const double v = prio[i];
+        if (v > m && v <= 1.7e308) m = v;
+    }
+    sm[threadIdx.x] = m;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (threadIdx.x < off && sm[threadIdx.x + off] > sm[threadIdx.x]) sm[threadIdx.x] = sm[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && sm[0] > *d.max_priority) *d.max_priority = sm[0];
 }
 
 /* Repair the sum / min trees above the n leaves idx[0..n) (entries < 0 are skipped) in ONE launch: a node is
@@ -260,13 +286,23 @@ __global__ void __launch_bounds__(1024) k_rp_fix_paths(ReplayDev d, const int32_
     int levels = 0;
     while ((1 << levels) < d.itcap) ++levels;
     for (int lv = 1; lv <= levels; ++lv) {
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            const int p = idx[i];
-            if (p < 0 || p >= d.cap) continue;
-            const int node = (d.itcap + p) >> lv;
-            d.sum[node] = d.sum[2 * node] + d.sum[2 * node + 1];
-            const double a = d.mn[2 * node], b = d.mn[2 * node + 1];
-            d.mn[node] = b < a ? b : a; /* Python min(a, b): b only if b < a */
+        const int width = d.itcap >> lv; /* nodes on this level */
+        if (width <= n) { /* near the root there are fewer nodes than touched leaves: recompute the level (same values, fewer loads) */
+            for (int i = threadIdx.x; i < width; i += blockDim.x) {
+                const int node = width + i;
+                d.sum[node] = d.sum[2 * node] + d.sum[2 * node + 1];
+                const double a = d.mn[2 * node], b = d.mn[2 * node + 1];
+                d.mn[node] = b < a ? b : a;
+            }
+        } else {
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                const int p = idx[i];
+                if (p < 0 || p >= d.cap) continue;
+                const int node = (d.itcap + p) >> lv;
+                d.sum[node] = d.sum[2 * node] + d.sum[2 * node + 1];
+                const double a = d.mn[2 * node], b = d.mn[2 * node + 1];
+                d.mn[node] = b < a ? b : a; /* Python min(a, b): b only if b < a */
+            }
         }
         __syncthreads();
     }
@@ -406,8 +442,9 @@ extern "C" int agar_replay_update_priorities(AgarReplay* rp, const int32_t* idx_
     if (!rp->d.prioritized || batch == 0) return AGAR_OK; /* ReplayBuffer.update_priorities is a no-op (:69-70) */
     RCU(cudaSetDevice(rp->device));
     cudaStream_t s = (cudaStream_t)stream;
-    k_rp_set_priorities<<<(batch + 127) / 128, 128, 0, s>>>(rp->d, idx_dev, priorities_dev, batch);
-    k_rp_max_priority<<<1, 1, 0, s>>>(rp->d, priorities_dev, batch);
+    const int staged = batch <= 12288; /* 48 KB of shared memory */
+    k_rp_set_priorities<<<(batch + 127) / 128, 128, staged ? (size_t)batch * 4 : 0, s>>>(rp->d, idx_dev, priorities_dev, batch, staged);
+    k_rp_max_priority<<<1, 256, 0, s>>>(rp->d, priorities_dev, batch);
     RCU(cudaGetLastError());
     rp->launches += 2;
     return rp_fix_paths(rp, idx_dev, batch, s);
