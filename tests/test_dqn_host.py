@@ -76,7 +76,7 @@ def test_dpg_critic_targets_equal_the_per_sample_loop():
         target = float(r[i])
         if int(done[i]) == 0:
             target += 0.9 * float(lrn.critic_target(s2[i:i + 1], lrn.actor_target(s2[i:i + 1]))[0])
-        est = float(lrn.critic(s[i:i + 1], a[i:i + 1])[0])
+        est = float(lrn.critic(s[i:i + 1], a[i:i + 1])[0].detach())
         assert abs(float(td[i]) - (target - est)) < 1e-5 and abs(float(q_old[i]) - est) < 1e-6
 
 

@@ -206,7 +206,8 @@ def test_host_buffer_path(torch_cuda):
 
 
 @pytest.mark.parametrize("kw,n", [(dict(), 64), (dict(num_nn=1, num_greedy=1, virus=True, split=True, eject=True), 24),
-                                  (dict(num_nn=2, num_greedy=1, virus=True, split=True, eject=True), 10)])
+                                  (dict(num_nn=2, num_greedy=1, virus=True, split=True, eject=True), 10),
+                                  (dict(num_nn=3, num_greedy=2, split=True, eject=True, grid_view=False), 14)])  # 12-float rows
 def test_host_buffer_path_pinned_groups(torch_cuda, kw, n):
     """The e2e path as bench.py drives it: PINNED caller buffers (the step kernel reads the actions in place, its CTAs store
     observations / reward / done straight into the caller's memory and raise the flag agar_step_host_end polls — one launch

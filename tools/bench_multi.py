@@ -1,5 +1,5 @@
 """Full 1000-frame rollouts of the multi-agent configs (steady state, not the first frames after a reset):
-python tools/bench_multi.py CONFIG ENVS [steps]   (run on a GPU box)"""
+python tools/bench_multi.py CONFIG ENVS [steps] [tile width]   (run on a GPU box)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -8,7 +8,8 @@ from aigar_b200.env import AgarBatch
 from sweep import KWS
 which, E = sys.argv[1], int(sys.argv[2])
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
-b = AgarBatch(lay.derive_config(**KWS[which]), E, seed=2026, first_env_id=3 * 10 ** 6)
+tile = int(sys.argv[4]) if len(sys.argv) > 4 else None
+b = AgarBatch(lay.derive_config(**KWS[which]), E, seed=2026, first_env_id=3 * 10 ** 6, **({"tile_width": tile} if tile else {}))
 b.rollout_random(125, 8, 0)
 torch.cuda.synchronize()
 ts = []
