@@ -10,7 +10,8 @@ from oracle import oracle as orc
 CONFIGS = [dict(), dict(num_nn=1, num_greedy=1, virus=True, split=True, eject=True),
            dict(num_nn=8, num_greedy=8, virus=True, split=True, eject=True),
            dict(num_nn=8, num_greedy=8, virus=False, split=True, eject=True),
-           dict(num_nn=2, num_random=1, split=True)]
+           dict(num_nn=2, num_random=1, split=True),
+           dict(grid_view=False), dict(num_nn=3, num_greedy=5, virus=True, split=True, eject=True, grid_view=False)]
 
 
 @pytest.mark.parametrize("kw", CONFIGS)
@@ -29,6 +30,8 @@ def test_sizes_match_the_survey():
         assert (L.field_size, L.pellet_cap, L.state_len) == (s, p, l)
     cfg = lay.derive_config(num_nn=8, num_greedy=8, virus=False, split=True, eject=True)
     assert lay.layout_for_config(cfg).state_len == 733
+    L = lay.layout_for_config(lay.derive_config(num_nn=2, num_greedy=2, split=True, eject=True, grid_view=False))
+    assert (L.state_len, L.n_grids, L.n_extra, L.n_hist) == (lay.SIMPLE_STATE_LEN, 0, 0, 0)  # bot.py:511-548: 12 values
 
 
 def test_invalid_configs_are_rejected():
