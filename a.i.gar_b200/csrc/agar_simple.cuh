@@ -356,7 +356,7 @@ DEV void s_field_update(SReg& r, const SPtr& q, const DevParams& P, uint32_t env
     update_pos(r.x, r.y, vx, vy, r.svx, r.svy, r.counter, S);
     r.flags |= AGAR_CF_INHASH;
     /* playerPelletOverlap (field.py:207-213): slot order, the cell grows as it eats.
-     * Phase 1: integer window |d| <= radius + 2 around the cell -> candidate bitmask over this lane's slots. */
+     * Phase 1: integer window |d| <= (int)radius + 1 around the cell -> candidate bitmask over this lane's slots. */
     /* The candidate rectangle is fixed before the cell grows (field.py:207).  While the cell has not grown this frame the
      * rectangle test is implied by the eat test — overlap with the cell as the bigger one puts the pellet's integer centre
      * strictly inside (x - r, x + r), i.e. inside the coordinates [bucket_left, limit - 1] the cell's buckets cover
@@ -366,7 +366,10 @@ DEV void s_field_update(SReg& r, const SPtr& q, const DevParams& P, uint32_t env
     const double cx = r.x, cy = r.y;
     const int icx = (int)cx, icy = (int)cy;
     const int cap = P.L.pellet_cap;
-    int reach = (int)radius + 2;
+    /* Window bound: a pellet that passes the eat test has d^2 * 1.1 < r^2, so |px - cx| <= d < 0.954 r, and with icx = floor(cx)
+     * |px - icx| < 0.954 r + 1, an integer: <= (int)r + 1.  The bound depends on (int)r only, so the candidate masks stay valid
+     * while the cell grows inside the same integer radius (round 1 used (int)r + 2: 1.5-2x more candidates to walk). */
+    int reach = (int)radius + 1;
     /* When the pool is full (the steady state: cap == refill target) the free slots after eating are exactly the
      * eaten ones, in ascending order — remember up to four and skip the free-slot search when respawning. */
     const bool pool_full = r.n_pellets == cap;
@@ -422,8 +425,8 @@ DEV void s_field_update(SReg& r, const SPtr& q, const DevParams& P, uint32_t env
                 else if (n_eaten == 2) eaten2 = first;
                 else if (n_eaten == 3) eaten3 = first;
                 n_eaten += 1;
-                if ((int)radius + 2 > reach) { /* the grown cell reaches farther: re-scan the slots after this one */
-                    reach = (int)radius + 2;
+                if ((int)radius + 1 > reach) { /* the grown cell reaches farther: re-scan the slots after this one */
+                    reach = (int)radius + 1;
                     scan(first + 1);
                 }
             }
