@@ -356,7 +356,7 @@ DEV void s_field_update(SReg& r, const SPtr& q, const DevParams& P, uint32_t env
     update_pos(r.x, r.y, vx, vy, r.svx, r.svy, r.counter, S);
     r.flags |= AGAR_CF_INHASH;
     /* playerPelletOverlap (field.py:207-213): slot order, the cell grows as it eats.
-     * Phase 1: integer window |d| <= (int)radius + 1 around the cell -> candidate bitmask over this lane's slots. */
+     * Phase 1: candidate filter around the cell -> bitmask over this lane's slots. */
     /* The candidate rectangle is fixed before the cell grows (field.py:207).  While the cell has not grown this frame the
      * rectangle test is implied by the eat test — overlap with the cell as the bigger one puts the pellet's integer centre
      * strictly inside (x - r, x + r), i.e. inside the coordinates [bucket_left, limit - 1] the cell's buckets cover
@@ -364,12 +364,21 @@ DEV void s_field_update(SReg& r, const SPtr& q, const DevParams& P, uint32_t env
      * pre-growth radius, for pellets met after the first one eaten in the frame. */
     const double radius0 = radius;
     const double cx = r.x, cy = r.y;
-    const int icx = (int)cx, icy = (int)cy;
     const int cap = P.L.pellet_cap;
-    /* Window bound: a pellet that passes the eat test has d^2 * 1.1 < r^2, so |px - cx| <= d < 0.954 r, and with icx = floor(cx)
-     * |px - icx| < 0.954 r + 1, an integer: <= (int)r + 1.  The bound depends on (int)r only, so the candidate masks stay valid
-     * while the cell grows inside the same integer radius (round 1 used (int)r + 2: 1.5-2x more candidates to walk). */
+    /* Candidate filter.  Tiles of <= 2 lanes (one conversion pipe for many slots per lane: the float form below costs 15 % at
+     * one lane per env): the integer window |p - floor(c)| <= (int)r + 1 per axis — a pellet that passes the eat test has
+     * d^2 * 1.1 < r^2, so |px - cx| <= d < 0.954 r and |px - icx| < 0.954 r + 1, an integer: <= (int)r + 1; the bound depends on
+     * (int)r only, so the masks stay valid while the cell grows inside the same integer radius.
+     * Tiles of >= 4 lanes: the eat test itself in float32 with slack.  The exact test needs d^2 <= 0.90910 r^2; the float32
+     * distance (px - (float)cx)^2 + (py - (float)cy)^2 differs from d^2 by less than 3e-3 for coordinates below 128 and d < 110
+     * (|dx| is off by <= 6e-6, three roundings of 2^-24), so "d2f <= 0.9101 (float)(r^2) + 0.1" admits every pellet the exact test
+     * can accept and almost nothing else (the window admits 0.9-1.8 candidates per env and frame, each one more trip of the
+     * ordered loop).  That bound follows the radius: the slots after an eaten pellet are always re-scanned. */
+    constexpr bool DISC = W >= 4;
+    const int icx = (int)cx, icy = (int)cy;
     int reach = (int)radius + 1;
+    const float cxf = (float)cx, cyf = (float)cy;
+    float thr = 0.9101f * (float)(radius * radius) + 0.1f;
     /* When the pool is full (the steady state: cap == refill target) the free slots after eating are exactly the
      * eaten ones, in ascending order — remember up to four and skip the free-slot search when respawning. */
     const bool pool_full = r.n_pellets == cap;
@@ -381,20 +390,18 @@ DEV void s_field_update(SReg& r, const SPtr& q, const DevParams& P, uint32_t env
         m0 = m1 = 0;
         const int split = min(cap, sub + MB * W);
         const unsigned r2 = (unsigned)(2 * reach);
+        auto test = [&](uint32_t pk, int s) {
+            if (DISC) {
+                const float dx = (float)AGAR_PELLET_X(pk) - cxf, dy = (float)AGAR_PELLET_Y(pk) - cyf;
+                return dx * dx + dy * dy <= thr && pk != 0 && s >= first_slot;
+            }
+            const int px = AGAR_PELLET_X(pk), py = AGAR_PELLET_Y(pk);
+            return (unsigned)(px - icx + reach) <= r2 && (unsigned)(py - icy + reach) <= r2 && pk != 0 && s >= first_slot;
+        };
         int j = 0;
-        for (int s = sub; s < split; s += W, ++j) { /* branch-free accumulation, two plain loops */
-            uint32_t pk = q.pel[s];
-            int px = AGAR_PELLET_X(pk), py = AGAR_PELLET_Y(pk);
-            bool in = (unsigned)(px - icx + reach) <= r2 && (unsigned)(py - icy + reach) <= r2 && pk != 0 && s >= first_slot;
-            m0 |= (MT)in << j;
-        }
+        for (int s = sub; s < split; s += W, ++j) m0 |= (MT)test(q.pel[s], s) << j; /* branch-free accumulation, two plain loops */
         j = 0;
-        for (int s = sub + MB * W; s < cap; s += W, ++j) {
-            uint32_t pk = q.pel[s];
-            int px = AGAR_PELLET_X(pk), py = AGAR_PELLET_Y(pk);
-            bool in = (unsigned)(px - icx + reach) <= r2 && (unsigned)(py - icy + reach) <= r2 && pk != 0 && s >= first_slot;
-            m1 |= (MT)in << j;
-        }
+        for (int s = sub + MB * W; s < cap; s += W, ++j) m1 |= (MT)test(q.pel[s], s) << j;
     };
     scan(0);
     while (s_any<W>((m0 | m1) != 0)) { /* one vote decides the (usual) frame without candidates: no find-first-set, no tile minimum */
@@ -425,7 +432,10 @@ DEV void s_field_update(SReg& r, const SPtr& q, const DevParams& P, uint32_t env
                 else if (n_eaten == 2) eaten2 = first;
                 else if (n_eaten == 3) eaten3 = first;
                 n_eaten += 1;
-                if ((int)radius + 1 > reach) { /* the grown cell reaches farther: re-scan the slots after this one */
+                if (DISC) { /* the grown cell reaches farther: re-scan the slots after this one */
+                    thr = 0.9101f * (float)(radius * radius) + 0.1f;
+                    scan(first + 1);
+                } else if ((int)radius + 1 > reach) {
                     reach = (int)radius + 1;
                     scan(first + 1);
                 }

@@ -62,15 +62,15 @@ def test_pellet_rectangle_closed_form():
 
 def test_eat_test_implies_shared_bucket():
     """k_simple skips the hash-rectangle test for the first pellet a cell eats in a frame: whenever the eat test passes
-    (cell.py:143-152 overlap with the cell as the bigger one) the pellet's rectangle meets the cell's (pre-growth) one; and its
-    candidate window is |p - floor(c)| <= int(r) + 1 per axis."""
+    (cell.py:143-152 overlap with the cell as the bigger one) the pellet's rectangle meets the cell's (pre-growth) one; and it
+    passes the kernel's float32 candidate filter."""
     lib = orc.load()
     rng = np.random.default_rng(5)
     a0, a1, c0, c1 = (ctypes.c_int() for _ in range(4))
     checked = 0
     for S in (75, 106, 300):
         for _ in range(6000):
-            mass = float(rng.uniform(4, 400))
+            mass = float(rng.choice([rng.uniform(4, 400), rng.uniform(400, 22500)]))
             r = float(np.sqrt(mass / np.pi))
             x, y = rng.uniform(0, S, 2)
             if rng.random() < 0.3:  # hug a wall or a bucket edge
@@ -88,8 +88,12 @@ def test_eat_test_implies_shared_bucket():
                 lib.oracle_axis_range(float(x), r, S, ctypes.byref(a0), ctypes.byref(a1))
                 lib.oracle_axis_range(float(y), r, S, ctypes.byref(c0), ctypes.byref(c1))
                 assert a0.value <= px // 20 <= a1.value and c0.value <= py // 20 <= c1.value, (S, mass, x, y, px, py)
-                # ... and it lies inside k_simple's integer candidate window |p - floor(c)| <= int(r) + 1
+                # ... and it passes both of k_simple's candidate filters (agar_simple.cuh, s_field_update): the integer window
                 assert abs(px - int(x)) <= int(r) + 1 and abs(py - int(y)) <= int(r) + 1, (mass, x, y, px, py)
+                # ... and the float32 disc
+                f = np.float32
+                dxf, dyf = f(px) - f(x), f(py) - f(y)
+                assert f(dxf * dxf) + f(dyf * dyf) <= f(0.9101) * f(r * r) + f(0.1), (mass, x, y, px, py)
     assert checked > 20000
 
 
