@@ -220,49 +220,45 @@ AGAR_HD double agar_atan2(double y, double x) {
         if (x > 0) return agar_copysign(ay / ax, y);
         return y > 0 ? AGAR_OPI : -AGAR_OPI;
     }
-    double u, du;
-    if (ay < ax) {
-        u = ay / ax;
-        const double v = u * ax, vv = fma(u, ax, -v);
-        du = ((ay - v) - vv) / ax;
-    } else {
-        u = ax / ay;
-        const double v = u * ay, vv = fma(u, ay, -v);
-        du = ((ax - v) - vv) / ay;
+    /* u = min / max with the residual of the division; the two octant halves run the same operations on swapped operands, so the
+     * operands are selected and the divisions exist once (lanes of a warp that sit in different octants stay converged) */
+    const int steep = !(ay < ax);
+    const double num = steep ? ax : ay, den = steep ? ay : ax;
+    const double u = num / den;
+    double du;
+    {
+        const double v = u * den, vv = fma(u, den, -v);
+        du = ((num - v) - vv) / den;
     }
     double z;
-    const int small = u < 0.0625;
-    if (x > 0 && ay < ax) { /* (i) atan(ay / ax) */
-        if (small) {
-            const double v = u * u;
-            const double P = fma(v, fma(v, fma(v, fma(v, fma(v, 0x1.375f08b31cbcep-4, -0x1.7458022b13c25p-4), 0x1.c71c6e5129a3bp-4),
-                                               -0x1.24924923f7603p-3), 0x1.99999999997fdp-3), -0x1.5555555555555p-2);
+    const int case_i = x > 0 && !steep; /* (i) atan(ay / ax) */
+    /* (ii) x > 0: pi/2 - atan(ax/ay)   (iii) x < 0, ax < ay: pi/2 + atan(ax/ay)   (iv) x < 0: pi - atan(ay/ax);
+     * a subtraction is the addition of the exactly negated operand, so one code path serves all three */
+    const int iii = x < 0 && ax < ay;
+    const double K0 = (x > 0 || iii) ? AGAR_HPI : AGAR_OPI, K1 = (x > 0 || iii) ? AGAR_HPI1 : AGAR_OPI1;
+    if (u < 0.0625) {
+        const double v = u * u;
+        const double P = fma(v, fma(v, fma(v, fma(v, fma(v, 0x1.375f08b31cbcep-4, -0x1.7458022b13c25p-4), 0x1.c71c6e5129a3bp-4),
+                                           -0x1.24924923f7603p-3), 0x1.99999999997fdp-3), -0x1.5555555555555p-2);
+        if (case_i) {
             z = u + fma(u * v, P, du);
         } else {
-            const int i = (int)(fma(u, 256.0, 4503599627370496.0) - 4503599627370496.0) - 16;
+            const double zz = (u * v) * P;
+            const double su = iii ? u : -u, sdu = iii ? du : -du, szz = iii ? zz : -zz;
+            const double t2 = K0 + su;
+            const double cor = (K0 - t2) + su;
+            z = (((cor + K1) + sdu) + szz) + t2;
+        }
+    } else {
+        const int i = (int)(fma(u, 256.0, 4503599627370496.0) - 4503599627370496.0) - 16;
+        if (case_i) {
             const double t3 = u - AGAR_ATAN_T(i, 0);
             const double v = du + t3;
             const double dv = fabs(t3) > fabs(du) ? (t3 - v) + du : (du - v) + t3;
             const double t2 = AGAR_ATAN_T(i, 2);
             const double poly = fma(v, fma(v, fma(v, AGAR_ATAN_T(i, 6), AGAR_ATAN_T(i, 5)), AGAR_ATAN_T(i, 4)), AGAR_ATAN_T(i, 3));
             z = fma(v, t2, fma(dv, t2, (v * v) * poly)) + AGAR_ATAN_T(i, 1);
-        }
-    } else {
-        /* (ii) x > 0: pi/2 - atan(ax/ay)   (iii) x < 0, ax < ay: pi/2 + atan(ax/ay)   (iv) x < 0: pi - atan(ay/ax);
-         * a subtraction is the addition of the exactly negated operand, so one code path serves all three */
-        const int iii = x < 0 && ax < ay;
-        const double K0 = (x > 0 || iii) ? AGAR_HPI : AGAR_OPI, K1 = (x > 0 || iii) ? AGAR_HPI1 : AGAR_OPI1;
-        if (small) {
-            const double v = u * u;
-            const double P = fma(v, fma(v, fma(v, fma(v, fma(v, 0x1.375f08b31cbcep-4, -0x1.7458022b13c25p-4), 0x1.c71c6e5129a3bp-4),
-                                               -0x1.24924923f7603p-3), 0x1.99999999997fdp-3), -0x1.5555555555555p-2);
-            const double zz = (u * v) * P;
-            const double su = iii ? u : -u, sdu = iii ? du : -du, szz = iii ? zz : -zz;
-            const double t2 = K0 + su;
-            const double cor = (K0 - t2) + su;
-            z = (((cor + K1) + sdu) + szz) + t2;
         } else {
-            const int i = (int)(fma(u, 256.0, 4503599627370496.0) - 4503599627370496.0) - 16;
             const double v = (u - AGAR_ATAN_T(i, 0)) + du;
             const double q = fma(v, fma(v, fma(v, fma(v, AGAR_ATAN_T(i, 6), AGAR_ATAN_T(i, 5)), AGAR_ATAN_T(i, 4)), AGAR_ATAN_T(i, 3)),
                                  AGAR_ATAN_T(i, 2));
