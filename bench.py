@@ -56,17 +56,52 @@ def profiled_kernel_facts(envs, frames):
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  NVML is read from a thread of this
+    process every 2 ms (nvidia_ml_py: the library nvidia-smi itself reads) — a spawned `nvidia-smi -lms 5` needs 0.1-0.3 s to
+    start, and the whole timed region is ~0.13 s: it delivered between 1 and 20 samples per run.  nvidia-smi remains the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    REASON_BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, index):
         self.index = index
         self.proc = None
         self.path = None
+        self.thread = None
+        self.samples = []
+        self.stop_flag = False
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:  # the CUDA ordinal is not the NVML index when CUDA_VISIBLE_DEVICES reorders devices: go through the UUID
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
+
+    def _poll(self, nv, h):
+        reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        while not self.stop_flag:
+            try:
+                self.samples.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), mx, int(reasons_fn(h))))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        try:
+            import threading
+            nv, h = self._nvml_handle()
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            self.thread = threading.Thread(target=self._poll, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
@@ -79,6 +114,18 @@ class ClockSampler(object):
 
     def stop(self):
         res = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            if self.samples:
+                sm = sorted(s[0] for s in self.samples)
+                bits = 0
+                for s in self.samples:
+                    bits |= s[2]
+                res = {"sm_mhz": float(sm[len(sm) // 2]), "sm_max_mhz": float(max(s[1] for s in self.samples)),
+                       "reasons": sorted(n for n, b in self.REASON_BITS.items() if bits & b), "samples": len(sm),
+                       "source": "NVML, 2 ms"}
+            return res
         if self.proc is None:
             return res
         try:
@@ -103,7 +150,8 @@ class ClockSampler(object):
             os.unlink(self.path)
             if sm:
                 sm.sort()
-                res = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+                res = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                       "source": "nvidia-smi -lms 5"}
         except Exception:
             pass
         return res
