@@ -728,13 +728,13 @@ extern "C" int agar_create(const AgarConfig* cfg, int n_envs, int device, uint64
     const char* wenv = getenv("AGAR_TILE_W");
     if (wenv && atoi(wenv) > 0) W = atoi(wenv);
     if (agar_set_tile_width(e, W) != AGAR_OK && agar_set_tile_width(e, 8) != AGAR_OK && agar_set_tile_width(e, 32) != AGAR_OK) {
-        strncpy(g_create_err, e->err, 255);
+        snprintf(g_create_err, sizeof g_create_err, "%s", e->err);
         cudaFree(e->state), cudaFree(e->deg_tab), free(e);
         return AGAR_E_NOMEM;
     }
     rc = launch_init(e, nullptr, 0, stream);
     if (rc != AGAR_OK) {
-        strncpy(g_create_err, e->err, 255);
+        snprintf(g_create_err, sizeof g_create_err, "%s", e->err);
         cudaFree(e->state), cudaFree(e->deg_tab), free(e);
         return rc;
     }
