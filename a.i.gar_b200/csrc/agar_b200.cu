@@ -463,7 +463,8 @@ static bool config_is_simple(const AgarConfig& c, const AgarLayout& L) {
     return c.n_players == 1 && c.bot_type[0] == AGAR_BOT_NN && !c.virus_enabled && !c.enable_split && !c.enable_eject &&
            L.cell_cap == 1 && !c.self_grid && !c.wall_grid && !c.enemy_grid && !c.virus_grid && !c.self_grid_lf &&
            !c.self_grid_slf && !c.enemy_grid_lf && !c.enemy_grid_slf && !c.use_last_action && !c.use_second_last_action &&
-           !c.use_last_fovsize && L.n_hist == 0 && !c.all_player_grid && !c.simple_state; /* the 12-value representation lives in the general kernel */
+           !c.use_last_fovsize && L.n_hist == 0 && !c.all_player_grid && !c.simple_state && /* the 12-value representation lives in the general kernel */
+           L.field_size < 128; /* the float32 candidate filter of k_simple's eat chain is analysed for coordinates below 128 (one player: 75) */
 }
 
 /* pick the launch shape for tile width W; returns false if one record does not fit in shared memory */
