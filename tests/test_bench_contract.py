@@ -29,3 +29,18 @@ def test_gpu_arm_has_no_cpu_fallback():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"], capture_output=True,
                          text=True, timeout=300, cwd=ROOT)
     assert out.returncode != 0 and "no CUDA device" in (out.stderr + out.stdout)
+
+
+def test_clock_sampler_degrades_without_a_gpu():
+    """ClockSampler reads NVML in-process (fallback: nvidia-smi); without a driver both are absent and the contract's `clocks`
+    object carries nulls instead of raising."""
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("GPU present")
+    sys.path.insert(0, ROOT)
+    import bench
+    s = bench.ClockSampler(0)
+    s.start()
+    res = s.stop()
+    assert set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(res) and res["reasons"] == []
